@@ -1,0 +1,43 @@
+# Build of the B200 D2Q9-BGK solver.
+#
+#   make            liblbm_b200.so (sm_100a CUDA + C ABI) and the d2q9-bgk host program
+#   make oracle     the CPU checker under oracle/ (test infrastructure; never linked into the product)
+#   make check      run d2q9-bgk on the shipped 128x128 case and compare with the golden fixture
+#                   (needs a GPU; the comparison is tests/check_outputs.py == check/check.py's rule)
+#   make clean
+#
+# nvcc cross-compiles for sm_100a without a GPU.
+
+NVCC      ?= /usr/local/cuda/bin/nvcc
+HOSTCC    := /usr/bin/gcc
+PKG       := lbm-asynchronous_b200
+CUDA_ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(CUDA_ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v
+LIB       := $(PKG)/liblbm_b200.so
+BIN       := $(PKG)/d2q9-bgk
+TOOLS     := $(PKG)/gen_channel
+
+all: $(LIB) $(BIN) $(TOOLS)
+
+$(LIB): $(PKG)/csrc/lbm_b200.cu $(PKG)/csrc/lbm_kernels.cuh include/lbm_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -shared $(PKG)/csrc/lbm_b200.cu -o $@ -lcudart 2> build/ptxas.log || (cat build/ptxas.log; exit 1)
+
+$(BIN): $(PKG)/host/d2q9-bgk.c include/lbm_b200.h $(LIB)
+	$(HOSTCC) -std=c99 -O2 -Wall -Wextra -D_POSIX_C_SOURCE=200809L -Iinclude $(PKG)/host/d2q9-bgk.c -o $@ \
+	    -L$(PKG) -llbm_b200 -Wl,-rpath,'$$ORIGIN' -lm
+
+$(PKG)/gen_channel: $(PKG)/host/gen_channel.c
+	$(HOSTCC) -std=c99 -O2 -Wall -Wextra $< -o $@
+
+oracle:
+	$(MAKE) -C oracle all ref
+
+check: all
+	cd build && ../$(BIN) ../tests/golden/inputs/input_128x128.params ../tests/golden/inputs/obstacles_128x128.dat \
+	  && python ../tests/check_outputs.py --golden ../tests/golden/128x128.npz --av-vels av_vels.dat --final-state final_state.dat
+
+clean:
+	rm -rf build $(LIB) $(BIN) $(TOOLS)
+
+.PHONY: all oracle check clean

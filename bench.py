@@ -1,0 +1,371 @@
+#!/usr/bin/env python3
+"""bench.py -- MLUPS of the D2Q9-BGK timestep on N B200s (and the reference's CPU arm beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # N=1: in-process
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]
+
+One "step" = one lattice-Boltzmann timestep over the whole grid (accelerate + propagate + rebound +
+collision + the step's av_velocity reduction, one kernel launch per slab).
+
+Workloads (BASELINE.json configs 4 and 5):
+  N = 1 : synthetic channel 8192 x 8192, Bernoulli(0.005) obstacles, SplitMix64 seed 42
+  N > 1 : weak scaling, 32768 columns x 4096 rows PER GPU (8 GPUs = 32768 x 32768), same generator;
+          row slabs, one process per GPU; the per-step halo exchange is done by the step kernel
+          itself (peer stores into the neighbour GPU's halo ring over NVLink) -- no NCCL on the data
+          path; torch.distributed only carries handles, barriers and the timing reduction.
+
+Prints ONE JSON line (rank 0).  `value` = cells * K / device time (CUDA events, max over ranks) with
+everything resident in HBM; `e2e` = the same metric through the public API from HOST buffers
+(obstacle map uploaded, lattice initialised, K steps, av_vels and the final-state moments downloaded
+to pinned host memory inside the timed region).  Timing hygiene: W >= 3 warm-up steps; the two
+lattices (4.8 GB at 8192^2) are far larger than L2 (126 MB), so every step streams from HBM.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+BYTES_PER_LUP = 72.0  # 9 fp32 read + 9 fp32 written per lattice update
+L2_BYTES = 126e6
+
+
+def measured_peak():
+    """HBM GB/s denominator: MEASURED_PEAKS.json (driver-written), else the profiling guide's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def known_traffic():
+    """DRAM bytes per launch of the step kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {
+                getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+            }
+            self.ok = True
+            while not self._stop_evt.is_set():
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    for bit, name in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(self.period)
+        except Exception:
+            self.ok = False
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# -------------------------------------------------------------------------------------------------
+# the reference's CPU implementation (oracle/_ref: the reference's own OpenMP program, built from
+# /root/reference by oracle/Makefile) on a bounded sample of the workload
+# -------------------------------------------------------------------------------------------------
+def run_reference_cpu(nx: int, rows: int, iters: int, threads: int | None = None):
+    """Runs oracle/_ref/d2q9-bgk-openmp on an nx x rows channel of the benchmark's generator for `iters`
+    steps; returns (MLUPS from the program's own 'Elapsed Compute time', seconds, kind).  Falls back to the
+    oracle's fused port when the prebuilt reference binary is absent."""
+    threads = threads or os.cpu_count() or 1
+    exe = os.path.join(ROOT, "oracle", "_ref", "d2q9-bgk-openmp")
+    gen = os.path.join(ROOT, "lbm-asynchronous_b200", "gen_channel")
+    if os.path.exists(exe) and os.path.exists(gen):
+        td = tempfile.mkdtemp(prefix="lbm_ref_")
+        try:
+            subprocess.run([gen, str(nx), str(rows), str(iters), "in.params", "in.obstacles"], cwd=td, check=True)
+            # the reference always writes final_state.dat (87 B of text per cell): send it to /dev/null
+            os.symlink("/dev/null", os.path.join(td, "final_state.dat"))
+            env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="true", OMP_PLACES="cores")  # OpenMP/env.sh:2-4
+            r = subprocess.run([exe, "in.params", "in.obstacles"], cwd=td, env=env, capture_output=True, text=True, check=True)
+            m = re.search(r"Elapsed Compute time:\s+([0-9.]+)", r.stdout)
+            secs = float(m.group(1))
+            return nx * rows * iters / secs / 1e6, secs, "reference"
+        finally:
+            shutil.rmtree(td, ignore_errors=True)
+    orc = entry.load_oracle()
+    pkg = entry.load_package()
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    p = orc.Params(nx, rows, iters, 10, 0.1, 0.005, 1.85)
+    obst = pkg.channel_obstacles(nx, rows)
+    a = orc.init_cells(p)
+    t0 = time.perf_counter()
+    orc.run_fused(p, obst, iters, cells=a)
+    secs = time.perf_counter() - t0
+    return nx * rows * iters / secs / 1e6, secs, "port"
+
+
+def reference_arm(args) -> int:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    nx = args.nx or (8192 if args.gpus == 1 else 32768)
+    ny = (args.ny or (8192 if args.gpus == 1 else 4096)) * (1 if args.gpus == 1 else args.gpus)
+    cores = os.cpu_count() or 1
+    # bounded sample: rows chosen so that (warm-up + K) steps are roughly 4e9 lattice updates
+    total_steps = args.steps + args.warmup
+    rows = int(4.0e9 / (nx * max(total_steps, 1)))
+    rows = max(64, min(2048, rows // 64 * 64))
+    run_reference_cpu(nx, rows, max(args.warmup, 1), cores)  # warm-up run (page cache, CPU clocks)
+    mlups, secs, kind = run_reference_cpu(nx, rows, args.steps, cores)
+    sample = f"{nx}x{rows} rows of the channel workload, {args.steps} steps, {cores} OpenMP threads"
+    line = {
+        "impl": "reference", "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, nx, ny, note="reference arm runs a bounded row sample on the host cores"),
+        "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(n_gpus: int, nx: int, ny: int | None, note: str | None = None):
+    if n_gpus == 1:
+        name = f"synthetic channel {nx}x{ny or 8192}, Bernoulli(0.005) obstacles, SplitMix64 seed 42 (BASELINE config 4)"
+    else:
+        name = (f"synthetic channel weak scaling {nx} x {ny} ({nx}x{(ny or 0) // n_gpus} per GPU, row slabs), "
+                "Bernoulli(0.005) obstacles, seed 42 (BASELINE config 5)")
+    c = {"workload": name, "nx": nx, "ny": ny, "physics": "reynolds_dim=10 density=0.1 accel=0.005 omega=1.85",
+         "cache": "inputs larger than L2 (two lattices of 36 B/cell each; 126 MB L2)"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# -------------------------------------------------------------------------------------------------
+# the GPU arm
+# -------------------------------------------------------------------------------------------------
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=0)
+    ap.add_argument("--ny", type=int, default=0, help="rows (N=1) or rows per GPU (N>1)")
+    ap.add_argument("--arith", default=os.environ.get("LBM_ARITH", "strict"), choices=["strict", "fast"])
+    ap.add_argument("--halo-mode", default="sync", choices=["sync", "async"])
+    ap.add_argument("--kernel", type=int, default=int(os.environ.get("LBM_KERNEL", "0")))
+    ap.add_argument("--block", type=int, default=int(os.environ.get("LBM_BLOCK", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            print(f"bench.py: --gpus {args.gpus} needs torchrun with {args.gpus} ranks", file=sys.stderr)
+            return 2
+        args.gpus = world
+    if not torch.cuda.is_available():
+        print("bench.py: no CUDA device; the product has no CPU path", file=sys.stderr)
+        return 2
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pkg = entry.load_package()
+    from lbm_asynchronous_b200.lattice import make_param
+    from lbm_asynchronous_b200.sharded import ShardedLattice
+
+    n = args.gpus
+    nx = args.nx or (8192 if n == 1 else 32768)
+    ny = (args.ny or (8192 if n == 1 else 4096)) * (1 if n == 1 else n)
+    cells = nx * ny
+    K, W = args.steps, args.warmup
+    param = make_param(nx, ny, K, 10, 0.1, 0.005, 1.85)
+    opts = dict(arith=args.arith, halo_mode=args.halo_mode, kernel=args.kernel, block=args.block)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident run: `value` ----
+    if n == 1:
+        obst = pkg.channel_obstacles(nx, ny)
+        lat = pkg.Lattice(param, obst, ngpus=1, **opts)
+        runner = lat
+    else:
+        sh = ShardedLattice(param, lambda r0, r1: pkg.channel_obstacles(nx, ny, row0=r0, row1=r1), local_rank, **opts)
+        lat = sh.slab
+        runner = sh
+    lat.set_stream(stream.cuda_stream)
+    runner.run(W)
+    runner.sync()
+    barrier()
+    launches0 = lat.kernel_launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    runner.run(K)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lat.kernel_launches - launches0
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    av = runner.av_vels()
+    if not np.all(np.isfinite(av)) or not (av > 0).all():
+        print("bench.py: av_vels of the timed run are not finite/positive: the run is invalid", file=sys.stderr)
+        return 3
+    mlups = cells * K / (ms * 1e-3) / 1e6
+    lat.set_stream(None)
+    if n == 1:
+        lat.close()
+    else:
+        sh.close()
+
+    # ---- end to end through the public API from host buffers: `e2e` ----
+    e2e = None
+    if not args.no_e2e:
+        if n == 1:
+            r0, r1 = 0, ny
+        else:
+            st = pkg.partition(ny, n)
+            r0, r1 = st[rank], st[rank + 1]
+        my_cells = (r1 - r0) * nx
+        obst_pinned = torch.empty((r1 - r0, nx), dtype=torch.int32, pin_memory=True)
+        obst_pinned.numpy()[:] = pkg.channel_obstacles(nx, ny, row0=r0, row1=r1)
+        outs = [torch.empty((r1 - r0, nx), dtype=torch.float32, pin_memory=True) for _ in range(4)]
+        barrier()
+        t0 = time.perf_counter()
+        if n == 1:
+            lat2 = pkg.Lattice(param, obst_pinned.numpy(), ngpus=1, **opts)
+            run2 = lat2
+        else:
+            sh2 = ShardedLattice(param, lambda a, b: obst_pinned.numpy(), local_rank, **opts)
+            lat2, run2 = sh2.slab, sh2
+        run2.run(K)
+        av2 = run2.av_vels()
+        import ctypes as C
+
+        from lbm_asynchronous_b200.capi import check, library
+
+        check(library().lbm_final_state(lat2._h, *[C.cast(o.data_ptr(), C.POINTER(C.c_float)) for o in outs]))
+        torch.cuda.synchronize()
+        barrier()
+        secs = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([secs], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t.item())
+        e2e = {"value": cells * K / secs / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": my_cells * 4 * n / K, "d2h_bytes_per_step": (my_cells * 16 * n + K * 8 * 3) / K,
+               "seconds": secs, "what": "lbm_create(host obstacles) + lbm_run(K) + lbm_av_vels + lbm_final_state to pinned host"}
+        if n == 1:
+            lat2.close()
+        else:
+            sh2.close()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    achieved = mlups * 1e6 * BYTES_PER_LUP / 1e9 / n  # per GPU, GB/s
+    traffic = known_traffic()
+    line = {
+        "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": n, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(n, nx, ny), arith=args.arith, halo_mode=args.halo_mode if n > 1 else None,
+                       kernel=args.kernel, block=args.block),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": BYTES_PER_LUP * cells / n, "kernel": "lbm::step_vec4_kernel",
+                     "per_gpu": True},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "e2e": e2e,
+    }
+    if n == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rows, iters = 2048, 20
+        try:
+            v, secs, kind = run_reference_cpu(nx, rows, iters, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "MLUPS", "cores": cores, "kind": kind, "seconds": secs,
+                                    "sample": f"{nx}x{rows} rows of the same channel workload, {iters} steps, OpenMP program of the reference"}
+        except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
+            line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": cores, "kind": "reference", "sample": f"failed: {ex}"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

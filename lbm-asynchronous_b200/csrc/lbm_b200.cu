@@ -1,0 +1,1151 @@
+// lbm_b200.cu -- host side of the C ABI declared in include/lbm_b200.h.
+//
+// Owns the device-resident state of one run (the reference's cells / tmp_cells / obstacles / av_vels,
+// SerialCode/d2q9-bgk.c:531-543,610) and drives the sm_100a kernels of lbm_kernels.cuh:
+//   * lattices: 2 x 9 SoA planes per row slab, row pitch a multiple of 32 floats;
+//   * obstacles: 1 bit per cell;
+//   * the `for tt` loop (SerialCode:166-169) as CUDA graphs of GRAPH_STEPS kernel nodes, the step
+//     index living in device memory so that one graph serves the whole run;
+//   * av_vels: exact integer sums of |u| per step kept on the device for the whole run, combined in
+//     a fixed way by the host afterwards (replaces the MPI_Reduce of MPI/d2q9-bgk.c:298-309);
+//   * several slabs: halo rings + flags in peer-mapped memory, written by the neighbour's step kernel
+//     (replaces MPI_Isend/Irecv/Waitall|Testall, MPI_Waitall/d2q9-bgk.c:225-253).
+// There is no CPU fallback anywhere in this file: without a CUDA device every compute entry point
+// returns LBM_ENODEVICE.
+#include "../../include/lbm_b200.h"
+#include "lbm_kernels.cuh"
+
+#include <unistd.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace lbm;
+
+namespace {
+
+constexpr int GRAPH_STEPS = 32;      // kernel nodes per graph (even: lattice parity is restored)
+constexpr uint32_t HANDLE_MAGIC = 0x4c424d48u; // "LBMH"
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e__ = (call);                                                                                  \
+        if (e__ != cudaSuccess)                                                                                    \
+            return fail(e__ == cudaErrorMemoryAllocation ? LBM_ENOMEM : LBM_ECUDA, "%s failed: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                                              \
+    } while (0)
+
+struct HaloHandle { // what lbm_halo_export writes (<= LBM_HALO_HANDLE_BYTES)
+    uint32_t magic;
+    int32_t pid;
+    int32_t device;
+    int32_t pitch;
+    int32_t ring;
+    int32_t pad;
+    uint64_t local_ptr; // valid inside process `pid` only
+    uint64_t bytes;
+    cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(HaloHandle) <= LBM_HALO_HANDLE_BYTES, "handle too large");
+
+struct Slab {
+    int device = 0;
+    int row0 = 0, row1 = 0, rows = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    float* lat[2] = {nullptr, nullptr}; // 9 planes x rows x pitch each
+    uint32_t* obst = nullptr;           // rows x opitch
+    unsigned long long* fluid_dev = nullptr;
+    long long fluid = 0;
+    // halo block: [south ring][north ring][flags: 2 x 16 u64]  (one allocation: one IPC handle)
+    char* halo_block = nullptr;
+    size_t halo_bytes = 0;
+    float* ring_s = nullptr;
+    float* ring_n = nullptr;
+    unsigned long long* flag_s = nullptr;
+    unsigned long long* flag_n = nullptr;
+    // the neighbours' sides facing me
+    float* peer_ring_s = nullptr;           // south neighbour's north ring
+    unsigned long long* peer_flag_s = nullptr;
+    float* peer_ring_n = nullptr;           // north neighbour's south ring
+    unsigned long long* peer_flag_n = nullptr;
+    void* ipc_open[2] = {nullptr, nullptr}; // mappings to close
+    int* ctrl = nullptr;
+    int* error = nullptr;
+    unsigned long long* sums = nullptr;
+    size_t sums_steps = 0;
+    unsigned long long* state_sums = nullptr; // SUM_WORDS u64 + 1 double
+    cudaGraphExec_t graph[2] = {nullptr, nullptr}; // by parity of the source lattice
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // launch geometry
+    int tw_shift = 0, nbx = 0, ngroups = 0, nxv = 0, block = 0, nslots = 1;
+    unsigned grid = 0;
+    bool vec4 = false;
+    int accel_row = -1;
+};
+
+} // namespace
+
+struct lbm_lattice {
+    lbm_param_t p;
+    lbm_options_t opt;
+    int nslabs = 0;          // slabs held by this process
+    int rank = 0, nranks = 1; // ring position of slab 0 / ring size (per-process mode), else 0 / nslabs
+    bool per_process = false;
+    bool connected = false;
+    bool interleaved = false; // some slabs share a device (and therefore a stream): step-major launches only
+    Slab* slabs = nullptr;
+    int pitch = 0, opitch = 0, ring = 2;
+    int cur = 0;             // which lattice holds the current state
+    long long steps_done = 0;
+    long long launches = 0;
+    long long run_first = 0; // absolute index of the first step of the last lbm_run
+    int run_iters = 0;
+    float w0 = 0, w1 = 0, w2 = 0;   // initial state, SerialCode:546-548
+    float w1a = 0, w2a = 0;         // accelerate_flow weights, SerialCode:222-223
+    unsigned long long timeout_ns = 30ull * 1000000000ull;
+    void (*kernel)(StepArgs) = nullptr;
+};
+
+namespace {
+
+// ---- kernel table -------------------------------------------------------------------------------
+typedef void (*step_fn)(StepArgs);
+
+template <bool STRICT, int HINT>
+step_fn vec4_by_block(int block, int minb)
+{
+    switch (block) {
+    case 128: return minb >= 4 ? step_vec4_kernel<STRICT, HINT, 128, 4> : step_vec4_kernel<STRICT, HINT, 128, 1>;
+    case 512: return step_vec4_kernel<STRICT, HINT, 512, 1>;
+    default: return minb >= 2 ? step_vec4_kernel<STRICT, HINT, 256, 2> : step_vec4_kernel<STRICT, HINT, 256, 1>;
+    }
+}
+template <bool STRICT>
+step_fn vec4_by_hint(int hint, int block, int minb)
+{
+    switch (hint) {
+    case 0: return vec4_by_block<STRICT, 0>(block, minb);
+    case 1: return vec4_by_block<STRICT, 1>(block, minb);
+    default: return vec4_by_block<STRICT, 2>(block, minb);
+    }
+}
+step_fn scalar_kernel(bool strict, int block)
+{
+    if (block == 128) return strict ? step_scalar_kernel<true, 128> : step_scalar_kernel<false, 128>;
+    return strict ? step_scalar_kernel<true, 256> : step_scalar_kernel<false, 256>;
+}
+
+// opt.kernel: 0 default; otherwise decimal digits  H M  ->  hint = H-1 (1..3), minb = M
+//   e.g. 10 = plain loads/stores, 21 = ld.nc.no_allocate, 32 = + st.cs with min-blocks 2; 99 = scalar kernel
+struct KernelChoice {
+    bool vec4;
+    int hint, block, minb;
+};
+KernelChoice choose_kernel(const lbm_options_t& o, int nx)
+{
+    KernelChoice k;
+    k.vec4 = (nx % 4 == 0) && o.kernel != 99;
+    k.hint = 2;
+    k.minb = 1;
+    k.block = (o.block == 128 || o.block == 256 || o.block == 512) ? o.block : 256;
+    if (o.kernel > 0 && o.kernel != 99) {
+        const int h = o.kernel / 10, m = o.kernel % 10;
+        if (h >= 1 && h <= 3) k.hint = h - 1;
+        k.minb = m;
+    }
+    if (!k.vec4 && k.block == 512) k.block = 256;
+    return k;
+}
+
+int next_pow2_shift(int v) // smallest s with (1<<s) >= v
+{
+    int s = 0;
+    while ((1 << s) < v) s++;
+    return s;
+}
+
+int check_device_available()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(LBM_ENODEVICE, "no CUDA device available (%s): this library has no CPU path",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    return LBM_OK;
+}
+
+// the reference's constants must be what the device code hard-wires
+bool constants_ok()
+{
+    volatile float c_sq = 1.f / 3.f, w0 = 4.f / 9.f, w1 = 1.f / 9.f, w2 = 1.f / 36.f;
+    volatile float c2 = 2.f * c_sq, c4 = 2.f * c_sq * c_sq;
+    auto bits = [](float f) {
+        uint32_t u;
+        memcpy(&u, &f, 4);
+        return u;
+    };
+    return bits(c_sq) == 0x3eaaaaabu && bits(w0) == 0x3ee38e39u && bits(w1) == 0x3de38e39u && bits(w2) == 0x3ce38e39u &&
+           bits(c2) == 0x3f2aaaabu && bits(c4) == 0x3e638e3au && bits(1.f / c_sq) == 0x40400000u &&
+           bits(1.f / c2) == 0x3fc00000u && bits(1.f / c4) == 0x408fffffu;
+}
+
+int validate_params(const lbm_param_t* p)
+{
+    if (!p) return fail(LBM_EINVAL, "params is NULL");
+    if (p->nx < 1 || p->ny < 2) return fail(LBM_EINVAL, "grid too small: nx=%d ny=%d (need nx >= 1, ny >= 2)", p->nx, p->ny);
+    if (static_cast<long long>(p->nx) + 32 > 0x7fffffffLL) return fail(LBM_EINVAL, "nx too large");
+    return LBM_OK;
+}
+
+size_t plane_floats(const lbm_lattice* L, const Slab& s) { return static_cast<size_t>(s.rows) * L->pitch; }
+
+void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
+{
+    s.vec4 = k.vec4;
+    s.block = k.block;
+    s.nxv = k.vec4 ? L->p.nx / 4 : L->p.nx;
+    int sh = next_pow2_shift(s.nxv);
+    const int bsh = next_pow2_shift(s.block);
+    if (sh > bsh) sh = bsh;
+    s.tw_shift = sh;
+    const int tw = 1 << sh, th = s.block >> sh;
+    s.nbx = (s.nxv + tw - 1) / tw;
+    s.ngroups = (s.rows + th - 1) / th;
+    s.grid = static_cast<unsigned>(s.nbx) * static_cast<unsigned>(s.ngroups);
+    // spread the per-step global atomics over several addresses when there are many CTAs
+    int slots = 1;
+    while (slots < 64 && static_cast<unsigned>(slots) * 1024u < s.grid) slots <<= 1;
+    s.nslots = slots;
+}
+
+int alloc_slab(lbm_lattice* L, Slab& s, const int* obst_rows_host)
+{
+    CU(cudaSetDevice(s.device));
+    CU(cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking));
+    s.stream = s.own_stream;
+    CU(cudaEventCreate(&s.ev0));
+    CU(cudaEventCreate(&s.ev1));
+    const size_t pf = plane_floats(L, s);
+    for (int i = 0; i < 2; i++) CU(cudaMalloc(&s.lat[i], pf * Q * sizeof(float)));
+    CU(cudaMalloc(&s.obst, static_cast<size_t>(s.rows) * L->opitch * sizeof(uint32_t)));
+    CU(cudaMemsetAsync(s.obst, 0, static_cast<size_t>(s.rows) * L->opitch * sizeof(uint32_t), s.stream));
+    CU(cudaMalloc(&s.fluid_dev, sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(s.fluid_dev, 0, sizeof(unsigned long long), s.stream));
+    CU(cudaMalloc(&s.ctrl, 4 * sizeof(int)));
+    CU(cudaMemsetAsync(s.ctrl, 0, 4 * sizeof(int), s.stream));
+    CU(cudaMalloc(&s.error, sizeof(int)));
+    CU(cudaMemsetAsync(s.error, 0, sizeof(int), s.stream));
+    CU(cudaMalloc(&s.state_sums, (SUM_WORDS + 1) * sizeof(unsigned long long)));
+
+    // initial state: every cell, obstacles included (SerialCode:551-567); both lattices
+    const float w[Q] = {L->w0, L->w1, L->w1, L->w1, L->w1, L->w2, L->w2, L->w2, L->w2};
+    for (int i = 0; i < 2; i++)
+        for (int k = 0; k < Q; k++) {
+            fill_kernel<<<592, 256, 0, s.stream>>>(s.lat[i] + k * pf, pf, w[k]);
+            L->launches++;
+        }
+    CU(cudaGetLastError());
+
+    // obstacle map: stage the int rows, pack to bits on the device, count fluid cells
+    {
+        const size_t n = static_cast<size_t>(s.rows) * L->p.nx;
+        int* staging = nullptr;
+        CU(cudaMalloc(&staging, n * sizeof(int)));
+        CU(cudaMemcpyAsync(staging, obst_rows_host, n * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+        const size_t warps = static_cast<size_t>(s.rows) * ((L->p.nx + 31) / 32);
+        const size_t blocks = (warps * 32 + 255) / 256;
+        pack_obstacles_kernel<<<static_cast<unsigned>(blocks), 256, 0, s.stream>>>(staging, s.obst, L->p.nx, s.rows,
+                                                                                    L->opitch, s.fluid_dev);
+        L->launches++;
+        CU(cudaGetLastError());
+        unsigned long long fl = 0;
+        CU(cudaMemcpyAsync(&fl, s.fluid_dev, sizeof fl, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+        CU(cudaFree(staging));
+        s.fluid = static_cast<long long>(fl);
+    }
+    return LBM_OK;
+}
+
+int alloc_halo(lbm_lattice* L, Slab& s)
+{
+    CU(cudaSetDevice(s.device));
+    const size_t ring_floats = static_cast<size_t>(L->ring) * 3 * L->pitch;
+    s.halo_bytes = 2 * ring_floats * sizeof(float) + 2 * 128;
+    CU(cudaMalloc(&s.halo_block, s.halo_bytes));
+    s.ring_s = reinterpret_cast<float*>(s.halo_block);
+    s.ring_n = s.ring_s + ring_floats;
+    s.flag_s = reinterpret_cast<unsigned long long*>(s.halo_block + 2 * ring_floats * sizeof(float));
+    s.flag_n = s.flag_s + 16;
+    CU(cudaMemsetAsync(s.flag_s, 0, 256, s.stream));
+    // both rings start in the uniform initial state (MPI_Testall_OptimizedVersion/d2q9-bgk.c:784-824):
+    // south ring holds planes 2,5,6; north ring planes 4,7,8
+    for (int slot = 0; slot < L->ring; slot++) {
+        float* rs = s.ring_s + static_cast<size_t>(slot) * 3 * L->pitch;
+        float* rn = s.ring_n + static_cast<size_t>(slot) * 3 * L->pitch;
+        fill_kernel<<<64, 256, 0, s.stream>>>(rs, L->pitch, L->w1);
+        fill_kernel<<<64, 256, 0, s.stream>>>(rs + L->pitch, 2 * static_cast<size_t>(L->pitch), L->w2);
+        fill_kernel<<<64, 256, 0, s.stream>>>(rn, L->pitch, L->w1);
+        fill_kernel<<<64, 256, 0, s.stream>>>(rn + L->pitch, 2 * static_cast<size_t>(L->pitch), L->w2);
+        L->launches += 4;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s.stream));
+    return LBM_OK;
+}
+
+void destroy_graphs(Slab& s)
+{
+    for (int i = 0; i < 2; i++)
+        if (s.graph[i]) {
+            cudaGraphExecDestroy(s.graph[i]);
+            s.graph[i] = nullptr;
+        }
+}
+
+StepArgs make_args(const lbm_lattice* L, const Slab& s, int src, int step_offset)
+{
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    const size_t pf = plane_floats(L, s);
+    for (int k = 0; k < Q; k++) {
+        a.in[k] = s.lat[src] + k * pf;
+        a.out[k] = s.lat[src ^ 1] + k * pf;
+    }
+    const bool halo = (L->per_process ? true : L->nslabs > 1);
+    a.halo = halo ? 1 : 0;
+    if (!halo) {
+        // periodic wrap in y inside the lattice (SerialCode:257-258): row 0 pulls from row ny-1, row ny-1 from row 0
+        const size_t last = static_cast<size_t>(s.rows - 1) * L->pitch;
+        a.wrap_s[0] = a.in[2] + last, a.wrap_s[1] = a.in[5] + last, a.wrap_s[2] = a.in[6] + last;
+        a.wrap_n[0] = a.in[4], a.wrap_n[1] = a.in[7], a.wrap_n[2] = a.in[8];
+    } else {
+        a.hs.recv_ring = s.ring_s, a.hs.send_ring = s.peer_ring_s, a.hs.wait = s.flag_s, a.hs.signal = s.peer_flag_s;
+        a.hn.recv_ring = s.ring_n, a.hn.send_ring = s.peer_ring_n, a.hn.wait = s.flag_n, a.hn.signal = s.peer_flag_n;
+    }
+    a.halo_wait = (L->opt.halo_mode == LBM_HALO_SYNC) ? 1 : 0;
+    a.ring = L->ring;
+    a.lag = (L->opt.halo_mode == LBM_HALO_SYNC) ? L->opt.halo_lag : 0;
+    a.ctas_per_row = static_cast<unsigned>(s.nbx);
+    a.slot_stride = 3ull * L->pitch;
+    a.timeout_ns = L->timeout_ns;
+    a.error = s.error;
+    a.obst = s.obst;
+    a.ctrl = s.ctrl;
+    a.sums = s.sums;
+    a.nslots = s.nslots;
+    a.step_offset = step_offset;
+    a.nx = L->p.nx, a.nxv = s.nxv, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
+    a.tw_shift = s.tw_shift, a.nbx = s.nbx, a.ngroups = s.ngroups;
+    a.accel_row = s.accel_row;
+    a.omega = L->p.omega, a.w1a = L->w1a, a.w2a = L->w2a;
+    return a;
+}
+
+int build_graph(lbm_lattice* L, Slab& s, int parity)
+{
+    CU(cudaSetDevice(s.device));
+    cudaGraph_t g;
+    CU(cudaGraphCreate(&g, 0));
+    cudaGraphNode_t prev = nullptr;
+    std::vector<StepArgs> args(GRAPH_STEPS);
+    for (int j = 0; j < GRAPH_STEPS; j++) {
+        args[j] = make_args(L, s, (parity + j) & 1, j);
+        void* kp[1] = {&args[j]};
+        cudaKernelNodeParams np;
+        memset(&np, 0, sizeof np);
+        np.func = reinterpret_cast<void*>(L->kernel);
+        np.gridDim = dim3(s.grid, 1, 1);
+        np.blockDim = dim3(s.block, 1, 1);
+        np.sharedMemBytes = 0;
+        np.kernelParams = kp;
+        cudaGraphNode_t node;
+        CU(cudaGraphAddKernelNode(&node, g, prev ? &prev : nullptr, prev ? 1 : 0, &np));
+        prev = node;
+    }
+    {
+        int* ctrl = s.ctrl;
+        int by = GRAPH_STEPS;
+        void* kp[2] = {&ctrl, &by};
+        cudaKernelNodeParams np;
+        memset(&np, 0, sizeof np);
+        np.func = reinterpret_cast<void*>(advance_ctrl_kernel);
+        np.gridDim = dim3(1, 1, 1);
+        np.blockDim = dim3(32, 1, 1);
+        np.kernelParams = kp;
+        cudaGraphNode_t node;
+        CU(cudaGraphAddKernelNode(&node, g, &prev, 1, &np));
+    }
+    cudaError_t e = cudaGraphInstantiate(&s.graph[parity], g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(LBM_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    return LBM_OK;
+}
+
+int ensure_sums(lbm_lattice* L, Slab& s, size_t steps)
+{
+    CU(cudaSetDevice(s.device));
+    if (steps > s.sums_steps) {
+        if (s.sums) CU(cudaFree(s.sums));
+        s.sums = nullptr;
+        size_t cap = s.sums_steps ? s.sums_steps : 1024;
+        while (cap < steps) cap *= 2;
+        CU(cudaMalloc(&s.sums, cap * s.nslots * SUM_WORDS * sizeof(unsigned long long)));
+        s.sums_steps = cap;
+        destroy_graphs(s); // the graphs hold the old pointer
+    }
+    CU(cudaMemsetAsync(s.sums, 0, steps * s.nslots * SUM_WORDS * sizeof(unsigned long long), s.stream));
+    return LBM_OK;
+}
+
+bool uses_halo(const lbm_lattice* L) { return L->per_process || L->nslabs > 1; }
+
+int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t* opt)
+{
+    L->p = *params;
+    if (opt)
+        L->opt = *opt;
+    else
+        lbm_default_options(&L->opt);
+    if (L->opt.arith != LBM_ARITH_STRICT && L->opt.arith != LBM_ARITH_FAST) return fail(LBM_EINVAL, "bad arith option %d", L->opt.arith);
+    if (L->opt.halo_mode != LBM_HALO_SYNC && L->opt.halo_mode != LBM_HALO_ASYNC) return fail(LBM_EINVAL, "bad halo_mode %d", L->opt.halo_mode);
+    if (L->opt.halo_lag < 0 || (L->opt.halo_lag & 1) || L->opt.halo_lag > 64)
+        return fail(LBM_EINVAL, "halo_lag must be even and in [0, 64], got %d", L->opt.halo_lag);
+    if (L->opt.halo_mode == LBM_HALO_ASYNC && L->opt.halo_lag != 0)
+        return fail(LBM_EINVAL, "halo_lag is only meaningful with LBM_HALO_SYNC");
+    L->pitch = (params->nx + 31) / 32 * 32;
+    L->opitch = L->pitch / 32;
+    L->ring = 2 * L->opt.halo_lag + 2;
+    // exactly the reference's expressions (float arithmetic, left to right)
+    L->w0 = params->density * 4.f / 9.f;  // SerialCode:546
+    L->w1 = params->density / 9.f;        // :547
+    L->w2 = params->density / 36.f;       // :548
+    L->w1a = params->density * params->accel / 9.f;  // :222
+    L->w2a = params->density * params->accel / 36.f; // :223
+    if (const char* t = getenv("LBM_HALO_TIMEOUT_MS")) {
+        const long long ms = atoll(t);
+        if (ms > 0) L->timeout_ns = static_cast<unsigned long long>(ms) * 1000000ull;
+    }
+    const KernelChoice k = choose_kernel(L->opt, params->nx);
+    const bool strict = L->opt.arith == LBM_ARITH_STRICT;
+    if (k.vec4)
+        L->kernel = strict ? vec4_by_hint<true>(k.hint, k.block, k.minb) : vec4_by_hint<false>(k.hint, k.block, k.minb);
+    else
+        L->kernel = scalar_kernel(strict, k.block);
+    for (int i = 0; i < L->nslabs; i++) slab_geometry(L, L->slabs[i], k);
+    return LBM_OK;
+}
+
+void free_slab(Slab& s)
+{
+    cudaSetDevice(s.device);
+    destroy_graphs(s);
+    for (int i = 0; i < 2; i++)
+        if (s.ipc_open[i]) cudaIpcCloseMemHandle(s.ipc_open[i]);
+    for (int i = 0; i < 2; i++) cudaFree(s.lat[i]);
+    cudaFree(s.obst);
+    cudaFree(s.fluid_dev);
+    cudaFree(s.halo_block);
+    cudaFree(s.ctrl);
+    cudaFree(s.error);
+    cudaFree(s.sums);
+    cudaFree(s.state_sums);
+    if (s.ev0) cudaEventDestroy(s.ev0);
+    if (s.ev1) cudaEventDestroy(s.ev1);
+    if (s.own_stream) cudaStreamDestroy(s.own_stream);
+    cudaGetLastError();
+}
+
+int check_error_flags(lbm_lattice* L)
+{
+    for (int i = 0; i < L->nslabs; i++) {
+        Slab& s = L->slabs[i];
+        CU(cudaSetDevice(s.device));
+        int e = 0;
+        CU(cudaMemcpyAsync(&e, s.error, sizeof e, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+        if (e) {
+            CU(cudaMemsetAsync(s.error, 0, sizeof(int), s.stream));
+            return fail(LBM_ETIMEOUT, "halo wait timed out on slab %d (rows %d..%d): a neighbour never delivered its row", i,
+                        s.row0, s.row1 - 1);
+        }
+    }
+    return LBM_OK;
+}
+
+// push this slab's boundary rows of the current lattice into the neighbours' rings (every slot) and
+// set their flags to "everything up to steps_done delivered": used after lbm_upload_cells
+int push_boundary_rows(lbm_lattice* L, Slab& s)
+{
+    CU(cudaSetDevice(s.device));
+    const size_t pf = plane_floats(L, s);
+    const float* base = s.lat[L->cur];
+    const int nx = L->p.nx;
+    const unsigned blocks = (nx + 255) / 256;
+    const size_t last = static_cast<size_t>(s.rows - 1) * L->pitch;
+    // my row 0 -> south neighbour's north ring: planes 4,7,8
+    push_row_kernel<<<blocks, 256, 0, s.stream>>>(base + 4 * pf, base + 7 * pf, base + 8 * pf, s.peer_ring_s, nx, L->pitch,
+                                                  L->ring, 3ull * L->pitch);
+    // my last row -> north neighbour's south ring: planes 2,5,6
+    push_row_kernel<<<blocks, 256, 0, s.stream>>>(base + 2 * pf + last, base + 5 * pf + last, base + 6 * pf + last,
+                                                  s.peer_ring_n, nx, L->pitch, L->ring, 3ull * L->pitch);
+    L->launches += 2;
+    CU(cudaGetLastError());
+    const unsigned long long v = static_cast<unsigned long long>(L->steps_done) * static_cast<unsigned>(s.nbx);
+    CU(cudaMemcpyAsync(s.peer_flag_s, &v, sizeof v, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemcpyAsync(s.peer_flag_n, &v, sizeof v, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    return LBM_OK;
+}
+
+} // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+void lbm_default_options(lbm_options_t* opt)
+{
+    if (!opt) return;
+    opt->arith = LBM_ARITH_STRICT;
+    opt->halo_mode = LBM_HALO_SYNC;
+    opt->halo_lag = 0;
+    opt->use_graph = 1;
+    opt->kernel = 0;
+    opt->block = 0;
+}
+
+const char* lbm_last_error(void) { return g_err; }
+
+int lbm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int lbm_partition(int ny, int nslabs, int* starts)
+{
+    if (!starts || nslabs < 1 || ny < 1) return fail(LBM_EINVAL, "lbm_partition: bad arguments");
+    const int base = ny / nslabs, rem = ny % nslabs;
+    int row = 0;
+    for (int r = 0; r < nslabs; r++) {
+        // the remainder rows go to the last slabs, so the last slab is never the smallest
+        const int rows = base + (r >= nslabs - rem ? 1 : 0);
+        starts[r] = row;
+        row += rows;
+        if (nslabs > 1) {
+            const int need = (r == nslabs - 1) ? 3 : 2;
+            if (rows < need)
+                return fail(LBM_EINVAL, "ny=%d is too small for %d slabs (slab %d would own %d rows, needs %d)", ny, nslabs, r,
+                            rows, need);
+        }
+    }
+    starts[nslabs] = ny;
+    return LBM_OK;
+}
+
+static int create_common(const lbm_param_t* params, const lbm_options_t* opt, int nslabs, const int* devices,
+                         const int* starts, const int* obstacles /* rows of slab 0 onwards, contiguous */, bool per_process,
+                         int rank, int nranks, lbm_lattice_t** out)
+{
+    if (!out) return fail(LBM_EINVAL, "out is NULL");
+    *out = nullptr;
+    int rc = validate_params(params);
+    if (rc) return rc;
+    if (!obstacles) return fail(LBM_EINVAL, "obstacles is NULL");
+    if (!constants_ok()) return fail(LBM_EINVAL, "host float arithmetic does not reproduce the reference's constants");
+    rc = check_device_available();
+    if (rc) return rc;
+    lbm_lattice* L = new (std::nothrow) lbm_lattice();
+    if (!L) return fail(LBM_ENOMEM, "out of host memory");
+    L->nslabs = nslabs;
+    L->per_process = per_process;
+    L->rank = rank;
+    L->nranks = nranks;
+    L->slabs = new (std::nothrow) Slab[nslabs];
+    if (!L->slabs) {
+        delete L;
+        return fail(LBM_ENOMEM, "out of host memory");
+    }
+    for (int i = 0; i < nslabs; i++) {
+        Slab& s = L->slabs[i];
+        s.device = devices[i];
+        s.row0 = starts[i];
+        s.row1 = starts[i + 1];
+        s.rows = s.row1 - s.row0;
+        const int g = params->ny - 2; // the driven row, SerialCode:226
+        s.accel_row = (g >= s.row0 && g < s.row1) ? g - s.row0 : -1;
+    }
+    rc = common_setup(L, params, opt);
+    for (int i = 0; i < nslabs && !rc; i++) {
+        Slab& s = L->slabs[i];
+        rc = alloc_slab(L, s, obstacles + static_cast<size_t>(s.row0 - starts[0]) * params->nx);
+        if (!rc && uses_halo(L)) rc = alloc_halo(L, s);
+    }
+    if (rc) {
+        char keep[sizeof g_err];
+        memcpy(keep, g_err, sizeof keep);
+        lbm_destroy(L);
+        memcpy(g_err, keep, sizeof keep);
+        return rc;
+    }
+    *out = L;
+    return LBM_OK;
+}
+
+int lbm_create_on(const lbm_param_t* params, const int* obstacles, int nslabs, const int* devices,
+                  const lbm_options_t* opt, lbm_lattice_t** out)
+{
+    if (nslabs < 1 || nslabs > 1024) return fail(LBM_EINVAL, "bad slab count %d", nslabs);
+    if (!devices) return fail(LBM_EINVAL, "devices is NULL");
+    int rc = validate_params(params);
+    if (rc) return rc;
+    rc = check_device_available();
+    if (rc) return rc;
+    const int ndev = lbm_device_count();
+    for (int i = 0; i < nslabs; i++)
+        if (devices[i] < 0 || devices[i] >= ndev)
+            return fail(LBM_ENODEVICE, "slab %d asks for CUDA device %d but only %d device(s) are visible", i, devices[i], ndev);
+    std::vector<int> starts(nslabs + 1);
+    rc = lbm_partition(params->ny, nslabs, starts.data());
+    if (rc) return rc;
+    lbm_lattice_t* L = nullptr;
+    rc = create_common(params, opt, nslabs, devices, starts.data(), obstacles, false, 0, nslabs, &L);
+    if (rc) return rc;
+    if (nslabs > 1) {
+        // slabs that share a device share a stream: their kernels then run one after the other in
+        // launch order, so a halo wait is always already satisfied (kernels that spin on one another
+        // must never depend on being co-resident on one GPU)
+        for (int i = 0; i < nslabs; i++)
+            for (int j = 0; j < i; j++)
+                if (L->slabs[j].device == L->slabs[i].device) {
+                    L->slabs[i].stream = L->slabs[j].stream;
+                    L->interleaved = true;
+                    break;
+                }
+        // peer access between neighbouring devices, then wire the ring (periodic: MPI/d2q9-bgk.c:253-254)
+        for (int i = 0; i < nslabs && !rc; i++) {
+            Slab& s = L->slabs[i];
+            Slab& south = L->slabs[(i - 1 + nslabs) % nslabs];
+            Slab& north = L->slabs[(i + 1) % nslabs];
+            for (Slab* nb : {&south, &north}) {
+                if (nb->device == s.device) continue;
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, s.device, nb->device);
+                if (!can) {
+                    rc = fail(LBM_ENODEVICE, "device %d cannot access device %d as a peer", s.device, nb->device);
+                    break;
+                }
+                cudaSetDevice(s.device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(nb->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    rc = fail(LBM_ECUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", s.device, nb->device, cudaGetErrorString(e));
+                    break;
+                }
+                cudaGetLastError();
+            }
+            s.peer_ring_s = south.ring_n, s.peer_flag_s = south.flag_n;
+            s.peer_ring_n = north.ring_s, s.peer_flag_n = north.flag_s;
+        }
+        if (rc) {
+            char keep[sizeof g_err];
+            memcpy(keep, g_err, sizeof keep);
+            lbm_destroy(L);
+            memcpy(g_err, keep, sizeof keep);
+            return rc;
+        }
+        L->connected = true;
+    } else {
+        L->connected = true;
+    }
+    *out = L;
+    return LBM_OK;
+}
+
+int lbm_create(const lbm_param_t* params, const int* obstacles, int ngpus, const lbm_options_t* opt, lbm_lattice_t** out)
+{
+    if (ngpus < 1) return fail(LBM_EINVAL, "ngpus must be >= 1, got %d", ngpus);
+    int rc = check_device_available();
+    if (rc) return rc;
+    const int ndev = lbm_device_count();
+    if (ngpus > ndev) return fail(LBM_ENODEVICE, "%d GPUs requested but only %d CUDA device(s) are visible", ngpus, ndev);
+    std::vector<int> devices(ngpus);
+    for (int i = 0; i < ngpus; i++) devices[i] = i;
+    return lbm_create_on(params, obstacles, ngpus, devices.data(), opt, out);
+}
+
+int lbm_create_slab(const lbm_param_t* params, const int* obstacle_rows, int row0, int row1, int rank, int nranks, int device,
+                    const lbm_options_t* opt, lbm_lattice_t** out)
+{
+    int rc = validate_params(params);
+    if (rc) return rc;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(LBM_EINVAL, "bad rank %d of %d", rank, nranks);
+    if (row0 < 0 || row1 > params->ny || row1 - row0 < 1) return fail(LBM_EINVAL, "bad row range [%d, %d)", row0, row1);
+    const int g = params->ny - 2;
+    if (nranks > 1 && g >= row0 && g < row1 && (g == row0 || g == row1 - 1))
+        return fail(LBM_EINVAL, "the driven row ny-2 must be an interior row of its slab (use lbm_partition)");
+    if (nranks == 1 && (row0 != 0 || row1 != params->ny)) return fail(LBM_EINVAL, "a single rank must own every row");
+    rc = check_device_available();
+    if (rc) return rc;
+    if (device < 0 || device >= lbm_device_count()) return fail(LBM_ENODEVICE, "CUDA device %d is not visible", device);
+    const int starts[2] = {row0, row1};
+    return create_common(params, opt, 1, &device, starts, obstacle_rows, true, rank, nranks, out);
+}
+
+int lbm_halo_export(lbm_lattice_t* L, void* handle)
+{
+    if (!L || !handle) return fail(LBM_EINVAL, "NULL argument");
+    if (!L->per_process) return fail(LBM_EINVAL, "lbm_halo_export is for lbm_create_slab lattices");
+    Slab& s = L->slabs[0];
+    HaloHandle h;
+    memset(&h, 0, sizeof h);
+    h.magic = HANDLE_MAGIC;
+    h.pid = static_cast<int32_t>(getpid());
+    h.device = s.device;
+    h.pitch = L->pitch;
+    h.ring = L->ring;
+    h.local_ptr = reinterpret_cast<uint64_t>(s.halo_block);
+    h.bytes = s.halo_bytes;
+    CU(cudaSetDevice(s.device));
+    CU(cudaIpcGetMemHandle(&h.ipc, s.halo_block));
+    memset(handle, 0, LBM_HALO_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof h);
+    return LBM_OK;
+}
+
+int lbm_halo_connect(lbm_lattice_t* L, const void* south_handle, const void* north_handle)
+{
+    if (!L || !south_handle || !north_handle) return fail(LBM_EINVAL, "NULL argument");
+    if (!L->per_process) return fail(LBM_EINVAL, "lbm_halo_connect is for lbm_create_slab lattices");
+    if (L->connected) return fail(LBM_EINVAL, "already connected");
+    Slab& s = L->slabs[0];
+    CU(cudaSetDevice(s.device));
+    HaloHandle h[2];
+    memcpy(&h[0], south_handle, sizeof(HaloHandle));
+    memcpy(&h[1], north_handle, sizeof(HaloHandle));
+    char* base[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; i++) {
+        if (h[i].magic != HANDLE_MAGIC) return fail(LBM_EINVAL, "neighbour handle %d is not a halo handle", i);
+        if (h[i].pitch != L->pitch || h[i].ring != L->ring || h[i].bytes != s.halo_bytes)
+            return fail(LBM_EINVAL, "neighbour %d was created with a different nx / halo_lag", i);
+        if (h[i].pid == static_cast<int32_t>(getpid())) {
+            base[i] = reinterpret_cast<char*>(h[i].local_ptr); // same process (e.g. a ring of one)
+            if (h[i].device != s.device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(h[i].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(LBM_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+        } else if (i == 1 && h[0].pid == h[1].pid && h[0].local_ptr == h[1].local_ptr && base[0]) {
+            base[1] = base[0]; // ring of two: both neighbours are the same rank
+        } else {
+            void* p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, h[i].ipc, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+                return fail(LBM_ENODEVICE, "cannot map the halo ring of the neighbour on device %d (pid %d): %s", h[i].device,
+                            h[i].pid, cudaGetErrorString(e));
+            s.ipc_open[i] = p;
+            base[i] = static_cast<char*>(p);
+        }
+    }
+    const size_t ring_floats = static_cast<size_t>(L->ring) * 3 * L->pitch;
+    auto ring_s_of = [&](char* b) { return reinterpret_cast<float*>(b); };
+    auto ring_n_of = [&](char* b) { return reinterpret_cast<float*>(b) + ring_floats; };
+    auto flag_s_of = [&](char* b) { return reinterpret_cast<unsigned long long*>(b + 2 * ring_floats * sizeof(float)); };
+    auto flag_n_of = [&](char* b) { return flag_s_of(b) + 16; };
+    // my south neighbour receives my row 0 in ITS north ring; my north neighbour my last row in ITS south ring
+    s.peer_ring_s = ring_n_of(base[0]), s.peer_flag_s = flag_n_of(base[0]);
+    s.peer_ring_n = ring_s_of(base[1]), s.peer_flag_n = flag_s_of(base[1]);
+    L->connected = true;
+    return LBM_OK;
+}
+
+int lbm_set_stream(lbm_lattice_t* L, void* cuda_stream)
+{
+    if (!L) return fail(LBM_EINVAL, "NULL lattice");
+    Slab& s0 = L->slabs[0];
+    cudaStream_t old = s0.stream;
+    cudaStream_t now = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s0.own_stream;
+    CU(cudaSetDevice(s0.device));
+    CU(cudaStreamSynchronize(old));
+    for (int i = 0; i < L->nslabs; i++)
+        if (L->slabs[i].stream == old) L->slabs[i].stream = now;
+    return LBM_OK;
+}
+
+int lbm_run(lbm_lattice_t* L, int iters)
+{
+    if (!L) return fail(LBM_EINVAL, "NULL lattice");
+    if (iters < 0) return fail(LBM_EINVAL, "iters must be >= 0");
+    if (!L->connected) return fail(LBM_EINVAL, "lbm_halo_connect has not been called");
+    if (L->steps_done + iters > 0x7ffffff0LL) return fail(LBM_EINVAL, "step counter would overflow");
+    L->run_first = L->steps_done;
+    L->run_iters = iters;
+    if (iters == 0) return LBM_OK;
+    const int first = static_cast<int>(L->steps_done);
+    for (int i = 0; i < L->nslabs; i++) {
+        Slab& s = L->slabs[i];
+        int rc = ensure_sums(L, s, static_cast<size_t>(iters));
+        if (rc) return rc;
+        set_ctrl_kernel<<<1, 32, 0, s.stream>>>(s.ctrl, first, first, first + iters - 1);
+        L->launches++;
+        if (i == 0) CU(cudaEventRecord(s.ev0, s.stream));
+        // accelerate_flow() of the first step (SerialCode:209); every later step's is applied by the
+        // previous step's store
+        if (s.accel_row >= 0) {
+            AccelArgs aa;
+            const size_t pf = plane_floats(L, s);
+            const size_t off = static_cast<size_t>(s.accel_row) * L->pitch;
+            for (int k = 0; k < Q; k++) aa.f[k] = s.lat[L->cur] + k * pf + off;
+            aa.obst_row = s.obst + static_cast<size_t>(s.accel_row) * L->opitch;
+            aa.nx = L->p.nx;
+            aa.w1a = L->w1a, aa.w2a = L->w2a;
+            accelerate_row_kernel<<<(L->p.nx + 255) / 256, 256, 0, s.stream>>>(aa);
+            L->launches++;
+        }
+        CU(cudaGetLastError());
+    }
+    int done = 0;
+    const int parity = L->cur;
+    if (L->opt.use_graph && !L->interleaved) {
+        while (iters - done >= GRAPH_STEPS) {
+            for (int i = 0; i < L->nslabs; i++) {
+                Slab& s = L->slabs[i];
+                if (!s.graph[parity]) {
+                    int rc = build_graph(L, s, parity);
+                    if (rc) return rc;
+                }
+                CU(cudaSetDevice(s.device));
+                CU(cudaGraphLaunch(s.graph[parity], s.stream));
+                L->launches += GRAPH_STEPS + 1;
+            }
+            done += GRAPH_STEPS;
+        }
+    }
+    const int rest = iters - done; // parity of `done` is even, so the source lattice is still `parity`
+    for (int j = 0; j < rest; j++) {
+        for (int i = 0; i < L->nslabs; i++) {
+            Slab& s = L->slabs[i];
+            CU(cudaSetDevice(s.device));
+            const StepArgs a = make_args(L, s, (parity + j) & 1, j);
+            L->kernel<<<s.grid, s.block, 0, s.stream>>>(a);
+            L->launches++;
+        }
+    }
+    for (int i = 0; i < L->nslabs; i++) {
+        Slab& s = L->slabs[i];
+        CU(cudaSetDevice(s.device));
+        if (rest) {
+            advance_ctrl_kernel<<<1, 32, 0, s.stream>>>(s.ctrl, rest);
+            L->launches++;
+        }
+        CU(cudaGetLastError());
+    }
+    // slab 0's stop event is recorded after it has seen every other slab's stream finish
+    for (int i = 1; i < L->nslabs; i++) {
+        Slab& s = L->slabs[i];
+        if (s.stream == L->slabs[0].stream) continue;
+        CU(cudaSetDevice(s.device));
+        CU(cudaEventRecord(s.ev1, s.stream));
+        CU(cudaSetDevice(L->slabs[0].device));
+        CU(cudaStreamWaitEvent(L->slabs[0].stream, s.ev1, 0));
+    }
+    CU(cudaSetDevice(L->slabs[0].device));
+    CU(cudaEventRecord(L->slabs[0].ev1, L->slabs[0].stream));
+    L->steps_done += iters;
+    L->cur = (parity + iters) & 1;
+    return LBM_OK;
+}
+
+int lbm_sync(lbm_lattice_t* L)
+{
+    if (!L) return fail(LBM_EINVAL, "NULL lattice");
+    for (int i = 0; i < L->nslabs; i++) {
+        Slab& s = L->slabs[i];
+        CU(cudaSetDevice(s.device));
+        CU(cudaStreamSynchronize(s.stream));
+    }
+    return check_error_flags(L);
+}
+
+int lbm_tot_u_sums(lbm_lattice_t* L, long long* sums, long long* nonfinite, int iters)
+{
+    if (!L || !sums) return fail(LBM_EINVAL, "NULL argument");
+    if (iters < 0 || iters > L->run_iters) return fail(LBM_EINVAL, "the last lbm_run call made %d steps, %d asked for", L->run_iters, iters);
+    int rc = lbm_sync(L);
+    if (rc) return rc;
+    for (int t = 0; t < iters; t++) {
+        sums[2 * t] = sums[2 * t + 1] = 0;
+        if (nonfinite) nonfinite[t] = 0;
+    }
+    std::vector<unsigned long long> host;
+    for (int i = 0; i < L->nslabs; i++) {
+        Slab& s = L->slabs[i];
+        CU(cudaSetDevice(s.device));
+        const size_t n = static_cast<size_t>(iters) * s.nslots * SUM_WORDS;
+        host.resize(n);
+        if (n) CU(cudaMemcpy(host.data(), s.sums, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (int t = 0; t < iters; t++)
+            for (int j = 0; j < s.nslots; j++) {
+                const unsigned long long* w = &host[(static_cast<size_t>(t) * s.nslots + j) * SUM_WORDS];
+                sums[2 * t] += static_cast<long long>(w[0]);
+                sums[2 * t + 1] += static_cast<long long>(w[1]);
+                if (nonfinite) nonfinite[t] += static_cast<long long>(w[2]);
+            }
+    }
+    return LBM_OK;
+}
+
+float lbm_av_from_sums(long long lo, long long hi, long long nonfinite, long long fluid_cells)
+{
+    if (nonfinite) return NAN;
+    // total = lo + hi * 2^24 in units of 2^-40: exact in 128-bit integers, rounded once to double,
+    // scaled (exactly) and rounded to the reference's float tot_u; then tot_u / (float)tot_cells as
+    // SerialCode/d2q9-bgk.c:457
+    const unsigned __int128 total = static_cast<unsigned __int128>(static_cast<unsigned long long>(lo)) +
+                                    (static_cast<unsigned __int128>(static_cast<unsigned long long>(hi)) << FIX_SPLIT);
+    const double hi64 = static_cast<double>(static_cast<unsigned long long>(total >> 64));
+    const double lo64 = static_cast<double>(static_cast<unsigned long long>(total));
+    const double tot = (hi64 * 18446744073709551616.0 + lo64) * (1.0 / 1099511627776.0);
+    const float tot_u = static_cast<float>(tot);
+    return tot_u / static_cast<float>(fluid_cells);
+}
+
+long long lbm_fluid_cells(const lbm_lattice_t* L)
+{
+    if (!L) return 0;
+    long long n = 0;
+    for (int i = 0; i < L->nslabs; i++) n += L->slabs[i].fluid;
+    return n;
+}
+
+long long lbm_steps_done(const lbm_lattice_t* L) { return L ? L->steps_done : 0; }
+
+int lbm_av_vels(lbm_lattice_t* L, float* av_vels, int iters)
+{
+    if (!L || !av_vels) return fail(LBM_EINVAL, "NULL argument");
+    if (L->per_process && L->nranks > 1)
+        return fail(LBM_EINVAL, "one slab per process: add lbm_tot_u_sums over the ranks and use lbm_av_from_sums");
+    std::vector<long long> sums(2 * static_cast<size_t>(iters > 0 ? iters : 0)), bad(iters > 0 ? iters : 0);
+    int rc = lbm_tot_u_sums(L, sums.data(), bad.data(), iters);
+    if (rc) return rc;
+    const long long fluid = lbm_fluid_cells(L);
+    for (int t = 0; t < iters; t++) av_vels[t] = lbm_av_from_sums(sums[2 * t], sums[2 * t + 1], bad[t], fluid);
+    return LBM_OK;
+}
+
+static int run_state_kernel(lbm_lattice_t* L, Slab& s, float* d_out[4], bool want_sums, bool want_density)
+{
+    StateArgs a;
+    memset(&a, 0, sizeof a);
+    const size_t pf = plane_floats(L, s);
+    for (int k = 0; k < Q; k++) a.f[k] = s.lat[L->cur] + k * pf;
+    a.obst = s.obst;
+    a.nx = L->p.nx, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
+    a.density = L->p.density;
+    a.u_x = d_out[0], a.u_y = d_out[1], a.u = d_out[2], a.pressure = d_out[3];
+    CU(cudaMemsetAsync(s.state_sums, 0, (SUM_WORDS + 1) * sizeof(unsigned long long), s.stream));
+    a.sums = want_sums ? s.state_sums : nullptr;
+    a.density_sum = want_density ? reinterpret_cast<double*>(s.state_sums + SUM_WORDS) : nullptr;
+    const size_t n = static_cast<size_t>(L->p.nx) * s.rows;
+    state_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s.stream>>>(a);
+    L->launches++;
+    CU(cudaGetLastError());
+    return LBM_OK;
+}
+
+int lbm_av_velocity(lbm_lattice_t* L, float* av)
+{
+    if (!L || !av) return fail(LBM_EINVAL, "NULL argument");
+    if (L->per_process && L->nranks > 1) return fail(LBM_EINVAL, "lbm_av_velocity needs a single-process lattice");
+    long long lo = 0, hi = 0, bad = 0;
+    for (int i = 0; i < L->nslabs; i++) {
+        Slab& s = L->slabs[i];
+        CU(cudaSetDevice(s.device));
+        float* none[4] = {nullptr, nullptr, nullptr, nullptr};
+        int rc = run_state_kernel(L, s, none, true, false);
+        if (rc) return rc;
+        unsigned long long w[SUM_WORDS];
+        CU(cudaMemcpyAsync(w, s.state_sums, sizeof w, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+        lo += static_cast<long long>(w[0]), hi += static_cast<long long>(w[1]), bad += static_cast<long long>(w[2]);
+    }
+    *av = lbm_av_from_sums(lo, hi, bad, lbm_fluid_cells(L));
+    return LBM_OK;
+}
+
+int lbm_total_density(lbm_lattice_t* L, double* total)
+{
+    if (!L || !total) return fail(LBM_EINVAL, "NULL argument");
+    double t = 0.0;
+    for (int i = 0; i < L->nslabs; i++) {
+        Slab& s = L->slabs[i];
+        CU(cudaSetDevice(s.device));
+        float* none[4] = {nullptr, nullptr, nullptr, nullptr};
+        int rc = run_state_kernel(L, s, none, false, true);
+        if (rc) return rc;
+        double d = 0.0;
+        CU(cudaMemcpyAsync(&d, s.state_sums + SUM_WORDS, sizeof d, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+        t += d;
+    }
+    *total = t;
+    return LBM_OK;
+}
+
+int lbm_final_state(lbm_lattice_t* L, float* u_x, float* u_y, float* u, float* pressure)
+{
+    if (!L) return fail(LBM_EINVAL, "NULL lattice");
+    int rc = lbm_sync(L);
+    if (rc) return rc;
+    float* host[4] = {u_x, u_y, u, pressure};
+    const int base_row = L->slabs[0].row0;
+    for (int i = 0; i < L->nslabs; i++) {
+        Slab& s = L->slabs[i];
+        CU(cudaSetDevice(s.device));
+        const size_t n = static_cast<size_t>(L->p.nx) * s.rows;
+        float* dev[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int q = 0; q < 4; q++)
+            if (host[q]) {
+                cudaError_t e = cudaMalloc(&dev[q], n * sizeof(float));
+                if (e != cudaSuccess) {
+                    for (int z = 0; z < q; z++) cudaFree(dev[z]);
+                    return fail(LBM_ENOMEM, "cudaMalloc of a final-state plane failed: %s", cudaGetErrorString(e));
+                }
+            }
+        rc = run_state_kernel(L, s, dev, false, false);
+        const size_t off = static_cast<size_t>(s.row0 - base_row) * L->p.nx;
+        for (int q = 0; q < 4 && !rc; q++)
+            if (host[q]) {
+                cudaError_t e = cudaMemcpyAsync(host[q] + off, dev[q], n * sizeof(float), cudaMemcpyDeviceToHost, s.stream);
+                if (e != cudaSuccess) rc = fail(LBM_ECUDA, "final-state download failed: %s", cudaGetErrorString(e));
+            }
+        cudaStreamSynchronize(s.stream);
+        for (int q = 0; q < 4; q++) cudaFree(dev[q]);
+        if (rc) return rc;
+    }
+    return LBM_OK;
+}
+
+static int layout_copy(lbm_lattice_t* L, lbm_speed_t* cells, bool download)
+{
+    int rc = lbm_sync(L);
+    if (rc) return rc;
+    const int base_row = L->slabs[0].row0;
+    for (int i = 0; i < L->nslabs; i++) {
+        Slab& s = L->slabs[i];
+        CU(cudaSetDevice(s.device));
+        const size_t n = static_cast<size_t>(L->p.nx) * s.rows;
+        float* aos = nullptr;
+        CU(cudaMalloc(&aos, n * Q * sizeof(float)));
+        LayoutArgs a;
+        const size_t pf = plane_floats(L, s);
+        for (int k = 0; k < Q; k++) a.f[k] = s.lat[L->cur] + k * pf;
+        a.aos = aos;
+        a.nx = L->p.nx, a.rows = s.rows, a.pitch = L->pitch;
+        float* host = reinterpret_cast<float*>(cells) + static_cast<size_t>(s.row0 - base_row) * L->p.nx * Q;
+        cudaError_t e;
+        if (download) {
+            soa_to_aos_kernel<<<1184, 256, 0, s.stream>>>(a);
+            e = cudaMemcpyAsync(host, aos, n * Q * sizeof(float), cudaMemcpyDeviceToHost, s.stream);
+        } else {
+            e = cudaMemcpyAsync(aos, host, n * Q * sizeof(float), cudaMemcpyHostToDevice, s.stream);
+            aos_to_soa_kernel<<<1184, 256, 0, s.stream>>>(a);
+        }
+        L->launches++;
+        cudaError_t e2 = cudaStreamSynchronize(s.stream);
+        cudaFree(aos);
+        if (e != cudaSuccess || e2 != cudaSuccess)
+            return fail(LBM_ECUDA, "cell %s failed: %s", download ? "download" : "upload",
+                        cudaGetErrorString(e != cudaSuccess ? e : e2));
+    }
+    return LBM_OK;
+}
+
+int lbm_download_cells(lbm_lattice_t* L, lbm_speed_t* cells)
+{
+    if (!L || !cells) return fail(LBM_EINVAL, "NULL argument");
+    return layout_copy(L, cells, true);
+}
+
+int lbm_upload_cells(lbm_lattice_t* L, const lbm_speed_t* cells)
+{
+    if (!L || !cells) return fail(LBM_EINVAL, "NULL argument");
+    if (!L->connected) return fail(LBM_EINVAL, "lbm_halo_connect has not been called");
+    int rc = layout_copy(L, const_cast<lbm_speed_t*>(cells), false);
+    if (rc) return rc;
+    if (uses_halo(L))
+        for (int i = 0; i < L->nslabs; i++) {
+            rc = push_boundary_rows(L, L->slabs[i]);
+            if (rc) return rc;
+        }
+    return LBM_OK;
+}
+
+int lbm_last_run_ms(lbm_lattice_t* L, float* ms)
+{
+    if (!L || !ms) return fail(LBM_EINVAL, "NULL argument");
+    int rc = lbm_sync(L);
+    if (rc) return rc;
+    if (L->run_iters == 0) {
+        *ms = 0.f;
+        return LBM_OK;
+    }
+    CU(cudaSetDevice(L->slabs[0].device));
+    CU(cudaEventElapsedTime(ms, L->slabs[0].ev0, L->slabs[0].ev1));
+    return LBM_OK;
+}
+
+long long lbm_kernel_launches(const lbm_lattice_t* L) { return L ? L->launches : 0; }
+
+int lbm_num_slabs(const lbm_lattice_t* L) { return L ? L->nslabs : 0; }
+
+int lbm_slab_info(const lbm_lattice_t* L, int i, int* row0, int* row1, int* device)
+{
+    if (!L || i < 0 || i >= L->nslabs) return fail(LBM_EINVAL, "bad slab index");
+    if (row0) *row0 = L->slabs[i].row0;
+    if (row1) *row1 = L->slabs[i].row1;
+    if (device) *device = L->slabs[i].device;
+    return LBM_OK;
+}
+
+void lbm_destroy(lbm_lattice_t* L)
+{
+    if (!L) return;
+    if (L->slabs) {
+        for (int i = 0; i < L->nslabs; i++) {
+            cudaSetDevice(L->slabs[i].device);
+            cudaDeviceSynchronize();
+        }
+        cudaGetLastError();
+        for (int i = 0; i < L->nslabs; i++) free_slab(L->slabs[i]);
+        delete[] L->slabs;
+    }
+    delete L;
+}
+
+} // extern "C"

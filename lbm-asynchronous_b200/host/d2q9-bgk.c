@@ -1,0 +1,237 @@
+/*
+ * d2q9-bgk -- host program of the B200 D2Q9-BGK lattice-Boltzmann solver.
+ *
+ * Same command line, input formats, output files and stdout lines as the reference programs
+ * (every variant of Xinran1205/LBM-Asynchronous shares them; cited below against
+ * SerialCode/d2q9-bgk.c), so the reference's check/check.py validates the results unchanged:
+ *
+ *     d2q9-bgk <paramfile> <obstaclefile>      ->  final_state.dat, av_vels.dat in the cwd
+ *
+ * All numerical work happens in liblbm_b200.so (include/lbm_b200.h) on the GPU(s); this file is
+ * plain C99 host glue: parse, call, time, print.  There is no CPU path: without a CUDA device the
+ * program stops with an error.
+ *
+ * Behaviour beyond the reference is selected by environment variables, so the command line stays
+ * the reference's:
+ *   LBM_GPUS=N               row slabs on N GPUs of this box (default 1)
+ *   LBM_HALO_MODE=sync|async halo protocol between slabs (sync == MPI_Waitall variant, async ==
+ *                            MPI_Testall variant: boundary rows never wait), default sync
+ *   LBM_HALO_LAG=k           sync only: deterministic staleness of k (even) steps
+ *   LBM_ARITH=strict|fast    collision arithmetic (default strict: bit-identical to SerialCode)
+ *   LBM_SKIP_FINAL_STATE=1   do not write final_state.dat (87 bytes per cell of text)
+ *   LBM_KERNEL, LBM_BLOCK    kernel variant / CTA size (tuning)
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+
+#include "lbm_b200.h"
+
+#define FINAL_STATE_FILE "final_state.dat" /* SerialCode/d2q9-bgk.c:62 */
+#define AV_VELS_FILE "av_vels.dat"         /* :63 */
+
+/* error convention of the reference: message on stderr, exit status 1 (SerialCode:745-751) */
+static void die(const char* message, const int line, const char* file)
+{
+    fprintf(stderr, "Error at line %d of file %s:\n", line, file);
+    fprintf(stderr, "%s\n", message);
+    fflush(stderr);
+    exit(EXIT_FAILURE);
+}
+#define DIE(msg) die((msg), __LINE__, __FILE__)
+
+static void usage(const char* exe) /* SerialCode:753-757 */
+{
+    fprintf(stderr, "Usage: %s <paramfile> <obstaclefile>\n", exe);
+    exit(EXIT_FAILURE);
+}
+
+static void die_lbm(const char* what, int line)
+{
+    char msg[768];
+    snprintf(msg, sizeof msg, "%s: %s", what, lbm_last_error());
+    die(msg, line, __FILE__);
+}
+#define LBM_CALL(call)                          \
+    do {                                        \
+        if ((call) != LBM_OK) die_lbm(#call, __LINE__); \
+    } while (0)
+
+static double wall_seconds(void)
+{
+    struct timeval t;
+    gettimeofday(&t, NULL);
+    return t.tv_sec + t.tv_usec / 1000000.0;
+}
+
+/* the seven values of the parameter file, in file order (SerialCode:480-506) */
+static void read_params(const char* path, lbm_param_t* p)
+{
+    FILE* fp = fopen(path, "r");
+    if (!fp) {
+        char msg[1024];
+        snprintf(msg, sizeof msg, "could not open input parameter file: %s", path);
+        DIE(msg);
+    }
+    struct {
+        const char* fmt;
+        void* dst;
+        const char* err;
+    } fields[7] = {
+        {"%d\n", &p->nx, "could not read param file: nx"},
+        {"%d\n", &p->ny, "could not read param file: ny"},
+        {"%d\n", &p->maxIters, "could not read param file: maxIters"},
+        {"%d\n", &p->reynolds_dim, "could not read param file: reynolds_dim"},
+        {"%f\n", &p->density, "could not read param file: density"},
+        {"%f\n", &p->accel, "could not read param file: accel"},
+        {"%f\n", &p->omega, "could not read param file: omega"},
+    };
+    for (int i = 0; i < 7; i++)
+        if (fscanf(fp, fields[i].fmt, fields[i].dst) != 1) DIE(fields[i].err);
+    fclose(fp);
+}
+
+/* obstacle file: lines `x y 1` until EOF; same checks and messages as SerialCode:588-601 */
+static int* read_obstacles(const char* path, const lbm_param_t* p)
+{
+    const size_t n = (size_t)p->nx * (size_t)p->ny;
+    int* obstacles = calloc(n, sizeof(int));
+    if (!obstacles) DIE("cannot allocate column memory for obstacles");
+    FILE* fp = fopen(path, "r");
+    if (!fp) {
+        char msg[1024];
+        snprintf(msg, sizeof msg, "could not open input obstacles file: %s", path);
+        DIE(msg);
+    }
+    int xx, yy, blocked, got;
+    while ((got = fscanf(fp, "%d %d %d\n", &xx, &yy, &blocked)) != EOF) {
+        if (got != 3) DIE("expected 3 values per line in obstacle file");
+        if (xx < 0 || xx > p->nx - 1) DIE("obstacle x-coord out of range");
+        if (yy < 0 || yy > p->ny - 1) DIE("obstacle y-coord out of range");
+        if (blocked != 1) DIE("obstacle blocked value should be 1");
+        obstacles[(size_t)xx + (size_t)yy * p->nx] = blocked;
+    }
+    fclose(fp);
+    return obstacles;
+}
+
+/* final_state.dat: `ii jj u_x u_y u pressure obstacle`, jj outer / ii inner (SerialCode:679-724);
+ * av_vels.dat: `tt:\tvalue` (:735-738) */
+static void write_final_state(const lbm_param_t* p, const int* obstacles, const float* ux, const float* uy, const float* u,
+                              const float* pressure)
+{
+    FILE* fp = fopen(FINAL_STATE_FILE, "w");
+    if (!fp) DIE("could not open file output file");
+    static char buf[1 << 20];
+    setvbuf(fp, buf, _IOFBF, sizeof buf);
+    for (int jj = 0; jj < p->ny; jj++)
+        for (int ii = 0; ii < p->nx; ii++) {
+            const size_t c = (size_t)ii + (size_t)jj * p->nx;
+            fprintf(fp, "%d %d %.12E %.12E %.12E %.12E %d\n", ii, jj, ux[c], uy[c], u[c], pressure[c], obstacles[c]);
+        }
+    fclose(fp);
+}
+
+static void write_av_vels(const lbm_param_t* p, const float* av_vels)
+{
+    FILE* fp = fopen(AV_VELS_FILE, "w");
+    if (!fp) DIE("could not open file output file");
+    for (int tt = 0; tt < p->maxIters; tt++) fprintf(fp, "%d:\t%.12E\n", tt, av_vels[tt]);
+    fclose(fp);
+}
+
+static int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+int main(int argc, char* argv[])
+{
+    if (argc != 3) usage(argv[0]);
+    const char* paramfile = argv[1];
+    const char* obstaclefile = argv[2];
+
+    /* ---- init: parse, create the device lattice (SerialCode:156-159) ---- */
+    const double tot_tic = wall_seconds();
+    lbm_param_t params;
+    read_params(paramfile, &params);
+    if (params.nx < 1 || params.ny < 2 || params.maxIters < 0) DIE("grid size / iteration count out of range");
+    int* obstacles = read_obstacles(obstaclefile, &params);
+
+    lbm_options_t opt;
+    lbm_default_options(&opt);
+    const char* s;
+    if ((s = getenv("LBM_ARITH")) && strcmp(s, "fast") == 0) opt.arith = LBM_ARITH_FAST;
+    if ((s = getenv("LBM_HALO_MODE")) && strcmp(s, "async") == 0) opt.halo_mode = LBM_HALO_ASYNC;
+    opt.halo_lag = env_int("LBM_HALO_LAG", 0);
+    opt.kernel = env_int("LBM_KERNEL", 0);
+    opt.block = env_int("LBM_BLOCK", 0);
+    opt.use_graph = env_int("LBM_GRAPH", 1);
+    const int ngpus = env_int("LBM_GPUS", 1);
+    const int skip_final = env_int("LBM_SKIP_FINAL_STATE", 0);
+
+    lbm_lattice_t* lat = NULL;
+    LBM_CALL(lbm_create(&params, obstacles, ngpus, &opt, &lat));
+    float* av_vels = malloc(sizeof(float) * (size_t)(params.maxIters > 0 ? params.maxIters : 1));
+    if (!av_vels) DIE("cannot allocate memory for av_vels");
+    LBM_CALL(lbm_sync(lat));
+    const double init_toc = wall_seconds();
+
+    /* ---- compute: the whole `for tt` loop runs on the device (SerialCode:166-169) ---- */
+    LBM_CALL(lbm_run(lat, params.maxIters));
+    LBM_CALL(lbm_sync(lat));
+    const double comp_toc = wall_seconds();
+
+    /* ---- collate: per-step sums -> av_vels, moments of the final state -> host (the MPI variants'
+     * gather + MPI_Reduce, MPI/d2q9-bgk.c:265-309) ---- */
+    LBM_CALL(lbm_av_vels(lat, av_vels, params.maxIters));
+    const size_t n = (size_t)params.nx * (size_t)params.ny;
+    float *ux = NULL, *uy = NULL, *u = NULL, *pressure = NULL;
+    if (!skip_final) {
+        ux = malloc(n * sizeof(float));
+        uy = malloc(n * sizeof(float));
+        u = malloc(n * sizeof(float));
+        pressure = malloc(n * sizeof(float));
+        if (!ux || !uy || !u || !pressure) DIE("cannot allocate memory for the final state");
+        LBM_CALL(lbm_final_state(lat, ux, uy, u, pressure));
+    }
+    float av_final = 0.f;
+    LBM_CALL(lbm_av_velocity(lat, &av_final));
+    float device_ms = 0.f;
+    LBM_CALL(lbm_last_run_ms(lat, &device_ms));
+    const double col_toc = wall_seconds();
+
+    /* ---- report (SerialCode:194-201); calc_reynolds :637-642 ---- */
+    const float viscosity = 1.f / 6.f * (2.f / params.omega - 1.f);
+    const float reynolds = av_final * params.reynolds_dim / viscosity;
+    printf("==done==\n");
+    printf("Reynolds number:\t\t%.12E\n", reynolds);
+    printf("Elapsed Init time:\t\t\t%.6lf (s)\n", init_toc - tot_tic);
+    printf("Elapsed Compute time:\t\t\t%.6lf (s)\n", comp_toc - init_toc);
+    printf("Elapsed Collate time:\t\t\t%.6lf (s)\n", col_toc - comp_toc);
+    printf("Elapsed Total time:\t\t\t%.6lf (s)\n", col_toc - tot_tic);
+    /* extra, machine-readable (after the reference's lines; 72 B per lattice update) */
+    if (params.maxIters > 0 && device_ms > 0.f) {
+        const double lups = (double)n * params.maxIters / (device_ms * 1e-3);
+        printf("B200: gpus=%d slabs=%d arith=%s halo=%s MLUPS=%.1f GB/s=%.1f kernel_ms_per_step=%.6f launches=%lld\n", ngpus,
+               lbm_num_slabs(lat), opt.arith == LBM_ARITH_STRICT ? "strict" : "fast",
+               opt.halo_mode == LBM_HALO_SYNC ? "sync" : "async", lups * 1e-6, lups * 72e-9, device_ms / params.maxIters,
+               lbm_kernel_launches(lat));
+    }
+    fflush(stdout);
+
+    if (!skip_final) write_final_state(&params, obstacles, ux, uy, u, pressure);
+    write_av_vels(&params, av_vels);
+
+    /* finalise (SerialCode:615-634) */
+    lbm_destroy(lat);
+    free(ux);
+    free(uy);
+    free(u);
+    free(pressure);
+    free(av_vels);
+    free(obstacles);
+    return EXIT_SUCCESS;
+}

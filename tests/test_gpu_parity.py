@@ -1,0 +1,364 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the reference's own outputs.
+
+Bars: the STRICT flavour is bit-exact on the lattice (integer compare of the fp32 bit patterns) --
+against the oracle on seeded inputs and against the SerialCode binary's final_state after the FULL
+40 000 / 80 000 / 20 000 steps of the shipped cases; av_vels is an exact integer reduction, compared
+with the oracle's double-precision sum of the same per-cell values (tolerance: 2^-41 per cell from
+the fixed-point rounding) and with the reference's sequential fp32 sum at rtol 5e-5 (summation
+order).  The FAST flavour is held to check.py's rule (1 %) against goldens and SerialCode, and to
+5e-3 % (pressure) on the full runs.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, INPUTS, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def load_case(orc, grid):
+    p = orc.read_params(os.path.join(INPUTS, f"input_{grid}.params"))
+    obst = orc.read_obstacles(os.path.join(INPUTS, f"obstacles_{grid}.dat"), p.nx, p.ny)
+    return p, obst
+
+
+def to_param(p, iters=None):
+    from lbm_asynchronous_b200.lattice import make_param
+
+    return make_param(p.nx, p.ny, p.max_iters if iters is None else iters, p.reynolds_dim, p.density, p.accel, p.omega)
+
+
+def random_case(orc, nx, ny, seed, p_obst=0.03, walls=True):
+    rng = np.random.default_rng(seed)
+    p = orc.Params(nx, ny, 0, 10, 0.1, 0.005, 1.85)
+    obst = (rng.random((ny, nx)) < p_obst).astype(np.int32)
+    if walls:
+        obst[0, :] = 1
+        obst[-1, :] = 1
+    if ny >= 2:
+        obst[ny - 2, :: max(1, nx // 5)] = 1  # a few blocked cells on the driven row too
+    cells = orc.init_cells(p)
+    cells *= (1 + 0.05 * rng.standard_normal(cells.shape)).astype(np.float32)
+    return p, obst, cells
+
+
+def assert_lattice_equal(cells, ref_cells, obst):
+    fluid = obst == 0
+    assert np.array_equal(bits(cells[fluid]), bits(ref_cells[fluid]))
+    # obstacle cells: speeds 1..8 hold the bounce-back values (speed 0 is a don't-care of the reference)
+    assert np.array_equal(bits(cells[~fluid][:, 1:]), bits(ref_cells[~fluid][:, 1:]))
+
+
+def exact_tot_u(orc, p, obst, cells_before, k):
+    """double-precision sum of the per-cell fp32 |u| after each of k steps (oracle)"""
+    out = []
+    c = cells_before
+    for _ in range(k):
+        c, _ = orc.run(p, obst, 1, cells=c)
+        out.append(orc.tot_u_f64(p, c, obst))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# strict flavour vs the oracle, seeded inputs, every kernel shape
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nx,ny,kernel,block", [
+    (128, 128, 0, 0), (128, 64, 10, 128), (256, 37, 21, 256), (512, 16, 32, 512), (1024, 9, 0, 256),
+    (64, 50, 0, 0), (32, 33, 0, 0), (8, 12, 0, 0), (4, 5, 0, 0),          # warps that span several rows
+    (100, 30, 0, 0), (36, 21, 0, 128), (2052, 7, 0, 0),                    # nx % 4 == 0 but not a power of two
+    (127, 20, 0, 0), (33, 17, 0, 128), (1, 8, 0, 0), (3, 3, 0, 0), (130, 2, 0, 0),  # scalar kernel
+    (128, 40, 99, 0),                                                       # scalar kernel forced
+])
+def test_strict_steps_bit_exact_vs_oracle(gpu, pkg, orc, nx, ny, kernel, block):
+    p, obst, cells0 = random_case(orc, nx, ny, seed=nx * 1000 + ny)
+    iters = 7
+    ref_cells, ref_av = orc.run(p, obst, iters, cells=cells0)
+    with pkg.Lattice(to_param(p, iters), obst, kernel=kernel, block=block) as lat:
+        lat.upload(cells0)
+        assert np.array_equal(bits(lat.cells()), bits(cells0))  # upload/download round trip
+        lat.run(iters)
+        cells = lat.cells()
+        av = lat.av_vels()
+        sums, bad = lat.tot_u_sums()
+        fluid = lat.fluid_cells
+    assert fluid == int((obst == 0).sum())
+    assert_lattice_equal(cells, ref_cells, obst)
+    assert not bad.any()
+    exact = exact_tot_u(orc, p, obst, cells0, iters)
+    for t in range(iters):
+        tot = (int(sums[t, 0]) + (int(sums[t, 1]) << 24)) * 2.0 ** -40
+        assert abs(tot - exact[t][0]) <= fluid * 2.0 ** -41 + 1e-12 * exact[t][0]
+        assert exact[t][1] == fluid
+    np.testing.assert_allclose(av, ref_av, rtol=5e-5)
+
+
+def test_chunked_runs_equal_one_run(gpu, pkg, orc):
+    """lbm_run may be called repeatedly: 3+1+40+33 steps (graph replays and single launches, odd and
+    even chunk lengths) == 77 steps, and the accelerate-at-store folding never leaks across calls."""
+    p, obst, cells0 = random_case(orc, 128, 48, seed=5)
+    ref_cells, ref_av = orc.run(p, obst, 77, cells=cells0)
+    with pkg.Lattice(to_param(p), obst) as lat:
+        lat.upload(cells0)
+        avs = []
+        for n in (3, 1, 40, 33):
+            lat.run(n)
+            avs.append(lat.av_vels())
+        assert lat.steps_done == 77
+        assert_lattice_equal(lat.cells(), ref_cells, obst)
+    np.testing.assert_allclose(np.concatenate(avs), ref_av, rtol=5e-5)
+
+
+def test_graph_and_plain_launch_paths_agree(gpu, pkg, orc):
+    p, obst, cells0 = random_case(orc, 256, 64, seed=6)
+    outs = []
+    for use_graph in (True, False):
+        with pkg.Lattice(to_param(p), obst, use_graph=use_graph) as lat:
+            lat.upload(cells0)
+            lat.run(100)
+            outs.append((lat.cells(), lat.tot_u_sums()[0]))
+    assert np.array_equal(bits(outs[0][0]), bits(outs[1][0]))
+    assert np.array_equal(outs[0][1], outs[1][1])  # integer sums: identical, not merely close
+
+
+def test_av_vels_identical_across_kernel_variants(gpu, pkg, orc):
+    """The |u| reduction is integer arithmetic per cell: every kernel variant / CTA shape gives the
+    same sums bit for bit."""
+    p, obst, cells0 = random_case(orc, 256, 40, seed=7)
+    ref = None
+    for kernel, block in [(0, 0), (10, 128), (21, 512), (99, 0), (99, 128)]:
+        with pkg.Lattice(to_param(p), obst, kernel=kernel, block=block) as lat:
+            lat.upload(cells0)
+            lat.run(9)
+            s = lat.tot_u_sums()[0]
+        ref = s if ref is None else ref
+        assert np.array_equal(s, ref)
+
+
+def test_state_queries_match_oracle(gpu, pkg, orc):
+    p, obst, cells0 = random_case(orc, 128, 32, seed=8)
+    with pkg.Lattice(to_param(p), obst) as lat:
+        lat.upload(cells0)
+        lat.run(5)
+        ux, uy, u, pr = lat.final_state()
+        cells = lat.cells()
+        av = lat.av_velocity()
+        dens = lat.total_density()
+        rey = lat.calc_reynolds()
+    rux, ruy, ru, rpr = orc.final_state(p, cells, obst)
+    for a, b in ((ux, rux), (uy, ruy), (u, ru), (pr, rpr)):
+        assert np.array_equal(bits(a), bits(b))
+    assert av == pytest.approx(orc.av_velocity(p, cells, obst), rel=5e-5)
+    assert dens == pytest.approx(float(cells.sum(dtype=np.float64)), rel=1e-9)
+    assert rey == pytest.approx(orc.calc_reynolds(p, cells, obst), rel=5e-5)
+
+
+def test_total_density_conserved_without_forcing(gpu, pkg, orc):
+    p, obst, cells0 = random_case(orc, 256, 64, seed=9)
+    p0 = p.replace(accel=0.0)
+    with pkg.Lattice(to_param(p0), obst) as lat:
+        lat.upload(cells0)
+        d0 = lat.total_density()
+        lat.run(200)
+        d1 = lat.total_density()
+    assert abs(d1 / d0 - 1) < 2e-6
+
+
+def test_nonfinite_cells_are_reported_not_hidden(gpu, pkg, orc):
+    p, obst, cells0 = random_case(orc, 64, 16, seed=10)
+    cells0[5, 7, :] = np.nan
+    with pkg.Lattice(to_param(p), obst) as lat:
+        lat.upload(cells0)
+        lat.run(1)
+        sums, bad = lat.tot_u_sums()
+        av = lat.av_vels()
+    assert bad[0] >= 1 and np.isnan(av[0])
+
+
+def test_invalid_arguments_are_rejected(gpu, pkg):
+    from lbm_asynchronous_b200.lattice import make_param
+
+    with pytest.raises(pkg.LbmError) as e:
+        pkg.Lattice(make_param(16, 1), np.zeros((1, 16), np.int32))
+    assert e.value.code == 1
+    with pytest.raises(pkg.LbmError) as e:
+        pkg.Lattice(make_param(16, 16), np.zeros((16, 16), np.int32), ngpus=1024)
+    assert e.value.code == 2
+    with pytest.raises(pkg.LbmError):
+        pkg.Lattice(make_param(16, 16), np.zeros((16, 16), np.int32), halo_lag=3)
+    with pkg.Lattice(make_param(16, 16), np.zeros((16, 16), np.int32)) as lat:
+        with pytest.raises(pkg.LbmError):
+            lat.run(-1)
+        lat.run(0)
+        assert lat.av_vels().size == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# the shipped cases at their full iteration counts, vs the SerialCode binary and the goldens
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("grid", ["128x128", "128x256", "256x256", "1024x1024"])
+def test_shipped_case_full_run_strict_is_bit_identical_to_serialcode(gpu, pkg, orc, grid):
+    import hashlib
+
+    p, obst = load_case(orc, grid)
+    fx = np.load(os.path.join(GOLDEN, f"{grid}.npz"))
+    with pkg.Lattice(to_param(p), obst, arith="strict") as lat:
+        lat.run(p.max_iters)
+        av = lat.av_vels()
+        ux, uy, u, pr = lat.final_state()
+        rey = lat.calc_reynolds()
+    assert np.array_equal(bits(pr), bits(fx["serial_pressure"]))
+    if "serial_ux" in fx:
+        assert np.array_equal(bits(ux), bits(fx["serial_ux"]))
+        assert np.array_equal(bits(uy), bits(fx["serial_uy"]))
+        assert np.array_equal(bits(u), bits(fx["serial_u"]))
+    else:
+        for name, plane in (("ux", ux), ("uy", uy), ("u", u)):
+            assert hashlib.sha256(plane.tobytes()).hexdigest() == str(fx[f"serial_{name}_sha256"])
+    # av_vels: same per-cell values, exact sum instead of a sequential (or per-thread) fp32 sum
+    np.testing.assert_allclose(av, fx["serial_av_vels"], rtol=1e-4)
+    assert rey == pytest.approx(float(fx["reynolds"]), rel=1e-4)
+    # check.py's rule against the reference's shipped (double precision) goldens
+    a = orc.check_metric(fx["golden_av_vels"], av)
+    assert np.isfinite(a) and abs(a) < 1.0
+    if "golden_pressure" in fx:
+        f = orc.check_metric(fx["golden_pressure"], pr.ravel())
+        assert np.isfinite(f) and abs(f) < 1.0
+
+
+@pytest.mark.parametrize("grid", ["128x128", "128x256", "256x256", "1024x1024"])
+def test_shipped_case_full_run_fast_passes_check(gpu, pkg, orc, grid):
+    p, obst = load_case(orc, grid)
+    fx = np.load(os.path.join(GOLDEN, f"{grid}.npz"))
+    with pkg.Lattice(to_param(p), obst, arith="fast") as lat:
+        lat.run(p.max_iters)
+        av = lat.av_vels()
+        _, _, _, pr = lat.final_state()
+    # vs the goldens: check.py's tolerance
+    a = orc.check_metric(fx["golden_av_vels"], av)
+    assert np.isfinite(a) and abs(a) < 1.0
+    if "golden_pressure" in fx:
+        assert abs(orc.check_metric(fx["golden_pressure"], pr.ravel())) < 1.0
+    # vs SerialCode: fp32 re-ordering noise only (-Ofast moves av_vels by <= 0.17 %)
+    assert abs(orc.check_metric(fx["serial_av_vels"], av)) < 0.5
+    assert abs(orc.check_metric(fx["serial_pressure"].ravel(), pr.ravel())) < 5e-3
+
+
+def test_first_steps_vs_serialcode_binary(gpu, pkg, orc):
+    for grid in ("128x128", "128x256"):
+        p, obst = load_case(orc, grid)
+        fx = np.load(os.path.join(GOLDEN, f"steps_{grid}.npz"))
+        for k in (1, 2, 3, 10, 101):
+            with pkg.Lattice(to_param(p, k), obst) as lat:
+                lat.run(k)
+                ux, uy, u, pr = lat.final_state()
+                av = lat.av_vels()
+            assert np.array_equal(bits(ux), bits(fx[f"ux_{k}"]))
+            assert np.array_equal(bits(uy), bits(fx[f"uy_{k}"]))
+            assert np.array_equal(bits(u), bits(fx[f"u_{k}"]))
+            assert np.array_equal(bits(pr), bits(fx[f"pressure_{k}"]))
+            np.testing.assert_allclose(av, fx[f"av_vels_{k}"], rtol=5e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# row slabs (several slabs on one device: the halo rings, flags and lag logic without needing N GPUs)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("grid,nslabs", [("128x128", 2), ("128x128", 5), ("128x256", 3), ("128x256", 8)])
+def test_slabs_sync_equal_single_lattice(gpu, pkg, orc, grid, nslabs):
+    """Sync halo mode == MPI_Waitall semantics: the decomposed run is bit-identical to the single
+    lattice (and, the sums being integers, so is av_vels)."""
+    p, obst = load_case(orc, grid)
+    iters = 150
+    with pkg.Lattice(to_param(p), obst) as lat:
+        lat.run(iters)
+        one = (lat.cells(), lat.tot_u_sums()[0])
+    with pkg.Lattice(to_param(p), obst, devices=[0] * nslabs) as lat:
+        assert len(lat.slabs()) == nslabs
+        lat.run(iters)
+        many = (lat.cells(), lat.tot_u_sums()[0])
+    assert np.array_equal(bits(one[0]), bits(many[0]))
+    assert np.array_equal(one[1], many[1])
+    ref_cells, _ = orc.run(p, obst, iters)
+    assert_lattice_equal(many[0], ref_cells, obst)
+
+
+def test_slabs_random_state_and_scalar_kernel(gpu, pkg, orc):
+    for nx, ny, n in [(128, 23, 4), (37, 19, 3), (4, 30, 7)]:
+        p, obst, cells0 = random_case(orc, nx, ny, seed=nx + ny, walls=False)  # periodic in y across the ring
+        ref_cells, _ = orc.run(p, obst, 11, cells=cells0)
+        with pkg.Lattice(to_param(p), obst, devices=[0] * n) as lat:
+            lat.upload(cells0)
+            lat.run(5)
+            lat.run(6)
+            assert_lattice_equal(lat.cells(), ref_cells, obst)
+
+
+@pytest.mark.parametrize("lag", [2, 4])
+def test_slabs_deterministic_stale_halo_equals_oracle(gpu, pkg, orc, lag):
+    """halo_lag=k: boundary rows at step t use the neighbour row of step t-k (initial state while
+    t < k) -- the oracle's restatement of the MPI_Testall variant's staleness model."""
+    p, obst = load_case(orc, "128x128")
+    iters = 90
+    nslabs = 4
+    starts = pkg.partition(p.ny, nslabs)
+    ref_cells, ref_av = orc.run_decomposed(p, obst, starts, lag, iters)
+    with pkg.Lattice(to_param(p), obst, devices=[0] * nslabs, halo_lag=lag) as lat:
+        assert [s[0] for s in lat.slabs()] == starts[:-1]
+        lat.run(iters)
+        cells = lat.cells()
+        av = lat.av_vels()
+    assert_lattice_equal(cells, ref_cells, obst)
+    np.testing.assert_allclose(av, ref_av, rtol=5e-5)
+    exact_cells, _ = orc.run(p, obst, iters)
+    assert not np.array_equal(bits(cells), bits(exact_cells))  # the lag really changes the result
+
+
+def test_slab_per_process_api_on_one_rank(gpu, pkg, orc):
+    """lbm_create_slab + export/connect with a ring of one (the slab is its own neighbour)."""
+    p, obst, cells0 = random_case(orc, 128, 24, seed=3, walls=False)
+    ref_cells, _ = orc.run(p, obst, 9, cells=cells0)
+    lat = pkg.SlabLattice(to_param(p), obst, 0, p.ny, 0, 1, 0)
+    with pytest.raises(pkg.LbmError):
+        lat.run(1)  # not connected yet
+    h = lat.export_handle()
+    lat.connect(h, h)
+    lat.upload(cells0)
+    lat.run(9)
+    assert_lattice_equal(lat.cells(), ref_cells, obst)
+    lat.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the host program, end to end, with check.py's rule
+# ---------------------------------------------------------------------------------------------
+def test_host_program_end_to_end(gpu, built, orc, tmp_path):
+    exe = os.path.join(ROOT, "lbm-asynchronous_b200", "d2q9-bgk")
+    grid = "128x128"
+    r = subprocess.run([exe, os.path.join(INPUTS, f"input_{grid}.params"), os.path.join(INPUTS, f"obstacles_{grid}.dat")],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0] == "==done=="
+    assert lines[1].startswith("Reynolds number:\t\t")
+    for i, name in enumerate(["Init", "Compute", "Collate", "Total"]):
+        assert lines[2 + i].startswith(f"Elapsed {name} time:\t\t\t") and lines[2 + i].endswith(" (s)")
+    fx = np.load(os.path.join(GOLDEN, f"{grid}.npz"))
+    assert float(lines[1].split()[-1]) == pytest.approx(float(fx["reynolds"]), rel=1e-4)
+    av = orc.read_av_vels(str(tmp_path / "av_vels.dat"))
+    fs = orc.read_final_state(str(tmp_path / "final_state.dat"))
+    ok, a, f = orc.check_passes(fx["golden_av_vels"], av, fx["golden_pressure"], fs[:, 5])
+    assert ok, (a, f)
+    # the text is the reference's: same lines as SerialCode's final_state.dat would hold
+    ny, nx = fx["serial_pressure"].shape
+    assert fs.shape == (nx * ny, 7)
+    assert np.array_equal(fs[:, 5].astype(np.float32).view(np.uint32), bits(fx["serial_pressure"]).ravel())
+    assert np.array_equal(fs[:, 2].astype(np.float32).view(np.uint32), bits(fx["serial_ux"]).ravel())
+    first = open(tmp_path / "final_state.dat").readline()
+    assert first == "0 0 0.000000000000E+00 0.000000000000E+00 0.000000000000E+00 3.333333507180E-02 1\n"
+    assert open(tmp_path / "av_vels.dat").readline().startswith("0:\t")
