@@ -19,7 +19,7 @@ TOOLS     := $(PKG)/gen_channel
 
 all: $(LIB) $(BIN) $(TOOLS)
 
-$(LIB): $(PKG)/csrc/lbm_b200.cu $(PKG)/csrc/lbm_kernels.cuh include/lbm_b200.h
+$(LIB): $(wildcard $(PKG)/csrc/*.cu $(PKG)/csrc/*.cuh) include/lbm_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -shared $(PKG)/csrc/lbm_b200.cu -o $@ -lcudart 2> build/ptxas.log || (cat build/ptxas.log; exit 1)
 

@@ -237,7 +237,10 @@ def main() -> int:
     K, W = args.steps, args.warmup
     param = make_param(nx, ny, K, 10, 0.1, 0.005, 1.85)
     opts = dict(arith=args.arith, halo_mode=args.halo_mode, kernel=args.kernel, block=args.block)
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream: the library runs its kernels on it (lbm_set_stream), the CUDA events
+    # below are recorded on it (handle 0, the legacy default stream, means "library's own stream")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
 
     def barrier():
         if dist is not None:

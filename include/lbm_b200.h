@@ -167,6 +167,11 @@ int lbm_upload_cells(lbm_lattice_t* lat, const lbm_speed_t* cells);
 int lbm_last_run_ms(lbm_lattice_t* lat, float* ms);
 /* kernels the library launched so far (graph nodes counted individually) */
 long long lbm_kernel_launches(const lbm_lattice_t* lat);
+/* Device self-test of the arithmetic building blocks of the strict flavour: the kernel's division and
+ * square-root sequences are compared with div.rn.f32 / sqrt.rn.f32 on about `pairs` pseudo-random
+ * operand sets drawn from the operand window they are specified for; mismatches[0] counts
+ * differing quotients, mismatches[1] differing roots.  Both must be 0. */
+int lbm_selftest(int device, unsigned long long pairs, unsigned long long seed, unsigned long long* mismatches /* [2] */);
 /* rows [row0,row1) and device of slab `i` (i < lbm_num_slabs) */
 int lbm_num_slabs(const lbm_lattice_t* lat);
 int lbm_slab_info(const lbm_lattice_t* lat, int i, int* row0, int* row1, int* device);

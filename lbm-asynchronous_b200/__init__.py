@@ -21,6 +21,7 @@ from .capi import (  # noqa: F401
     library,
     library_path,
     partition,
+    selftest,
 )
 from .lattice import Lattice, SlabLattice, av_from_sums  # noqa: F401
 from .synthetic import channel_obstacles, channel_params  # noqa: F401

@@ -21,7 +21,7 @@ SYMBOLS = (
     "lbm_create_slab", "lbm_halo_export", "lbm_halo_connect", "lbm_set_stream", "lbm_run", "lbm_sync", "lbm_av_vels",
     "lbm_tot_u_sums", "lbm_av_from_sums", "lbm_fluid_cells", "lbm_steps_done", "lbm_av_velocity", "lbm_total_density",
     "lbm_final_state", "lbm_download_cells", "lbm_upload_cells", "lbm_last_run_ms", "lbm_kernel_launches",
-    "lbm_num_slabs", "lbm_slab_info", "lbm_destroy",
+    "lbm_num_slabs", "lbm_slab_info", "lbm_destroy", "lbm_selftest",
 )
 
 
@@ -106,6 +106,7 @@ def library() -> C.CDLL:
         "lbm_num_slabs": (C.c_int, [vp]),
         "lbm_slab_info": (C.c_int, [vp, C.c_int, ip, ip, ip]),
         "lbm_destroy": (None, [vp]),
+        "lbm_selftest": (C.c_int, [C.c_int, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -119,6 +120,13 @@ def library() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != OK:
         raise LbmError(rc, library().lbm_last_error().decode("utf-8", "replace"))
+
+
+def selftest(pairs: int = 1 << 30, seed: int = 1, device: int = 0):
+    """lbm_selftest: (differing quotients, differing roots) over ~`pairs` random operand sets; both must be 0."""
+    out = (C.c_ulonglong * 2)()
+    check(library().lbm_selftest(device, pairs, seed, out))
+    return int(out[0]), int(out[1])
 
 
 def partition(ny: int, nslabs: int):

@@ -14,7 +14,9 @@
 // returns LBM_ENODEVICE.
 #include "../../include/lbm_b200.h"
 #include "lbm_kernels.cuh"
+#include "lbm_tma_kernel.cuh"
 
+#include <cudaTypedefs.h>
 #include <unistd.h>
 
 #include <cmath>
@@ -93,11 +95,18 @@ struct Slab {
     unsigned long long* state_sums = nullptr; // SUM_WORDS u64 + 1 double
     cudaGraphExec_t graph[2] = {nullptr, nullptr}; // by parity of the source lattice
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // launch geometry
+    // launch geometry of step_vec4_kernel / step_scalar_kernel
     int tw_shift = 0, nbx = 0, ngroups = 0, nxv = 0, block = 0, nslots = 1;
-    unsigned grid = 0;
+    unsigned grid = 0;    // every row (mode 0)
+    unsigned grid_b = 0;  // boundary rows only (mode 1)
     bool vec4 = false;
     int accel_row = -1;
+    // interior rows through step_tma_kernel
+    bool use_tma = false;
+    CUtensorMap tmap[2];  // per lattice: boxes TMA_TX wide
+    CUtensorMap tmapw[2]; // per lattice: boxes TMA_TXW wide (x-shifted planes)
+    int tma_ntx = 0, tma_ntiles = 0, tma_dq = 0, tma_dr = 0;
+    unsigned tma_grid = 0;
 };
 
 } // namespace
@@ -120,7 +129,10 @@ struct lbm_lattice {
     float w0 = 0, w1 = 0, w2 = 0;   // initial state, SerialCode:546-548
     float w1a = 0, w2a = 0;         // accelerate_flow weights, SerialCode:222-223
     unsigned long long timeout_ns = 30ull * 1000000000ull;
-    void (*kernel)(StepArgs) = nullptr;
+    void (*kernel)(StepArgs) = nullptr;                 // all rows, or the boundary rows next to step_tma_kernel
+    void (*tma_kernel)(CUtensorMap, CUtensorMap, TmaArgs) = nullptr; // interior rows (null: `kernel` does every row)
+    int tma_ty = 0, tma_stages = 0, tma_minb = 0, tma_resident = 0, sm_count = 0;
+    size_t tma_smem = 0;
 };
 
 namespace {
@@ -152,20 +164,61 @@ step_fn scalar_kernel(bool strict, int block)
     return strict ? step_scalar_kernel<true, 256> : step_scalar_kernel<false, 256>;
 }
 
-// opt.kernel: 0 default; otherwise decimal digits  H M  ->  hint = H-1 (1..3), minb = M
-//   e.g. 10 = plain loads/stores, 21 = ld.nc.no_allocate, 32 = + st.cs with min-blocks 2; 99 = scalar kernel
+typedef void (*tma_fn)(CUtensorMap, CUtensorMap, TmaArgs);
+struct TmaChoice {
+    int ty, stages, minb;
+    tma_fn fn;
+};
+template <bool STRICT>
+bool tma_by_shape(int ty, int stages, int minb, TmaChoice* c)
+{
+#define LBM_TMA_CASE(TY_, ST_, MB_)                               \
+    if (ty == TY_ && stages == ST_ && minb == MB_) {              \
+        *c = {TY_, ST_, MB_, step_tma_kernel<STRICT, TY_, ST_, MB_>}; \
+        return true;                                              \
+    }
+    LBM_TMA_CASE(8, 2, 3)
+    LBM_TMA_CASE(8, 2, 2)
+    LBM_TMA_CASE(8, 3, 2)
+    LBM_TMA_CASE(8, 3, 1)
+    LBM_TMA_CASE(8, 4, 1)
+    LBM_TMA_CASE(4, 3, 4)
+    LBM_TMA_CASE(4, 4, 4)
+    LBM_TMA_CASE(4, 4, 3)
+    LBM_TMA_CASE(4, 6, 2)
+    LBM_TMA_CASE(16, 2, 1)
+    LBM_TMA_CASE(16, 3, 1)
+#undef LBM_TMA_CASE
+    return false;
+}
+
+// opt.kernel:
+//   0            library default: step_tma_kernel (TY 8, 3 stages) for the interior rows when nx % 4 == 0,
+//                nx >= 128 and the slab has >= 3 rows, step_vec4_kernel / step_scalar_kernel otherwise
+//   1TTSM        step_tma_kernel with TT rows per tile, S stages, M resident CTAs per SM asked of the compiler
+//                (10823 10822 10832 10831 10841 10434 10444 10443 10462 11621 11631)
+//   H M (10..39) step_vec4_kernel for every row: hint = H-1 (0 plain, 1 ld.nc.no_allocate, 2 + st.cs), min blocks M
+//   99           step_scalar_kernel for every row
 struct KernelChoice {
     bool vec4;
     int hint, block, minb;
+    bool tma;
+    int tma_ty, tma_stages, tma_minb;
 };
 KernelChoice choose_kernel(const lbm_options_t& o, int nx)
 {
     KernelChoice k;
     k.vec4 = (nx % 4 == 0) && o.kernel != 99;
-    k.hint = 2;
+    k.hint = 0;
     k.minb = 1;
     k.block = (o.block == 128 || o.block == 256 || o.block == 512) ? o.block : 256;
-    if (o.kernel > 0 && o.kernel != 99) {
+    k.tma = k.vec4 && nx >= TMA_TX && (o.kernel == 0 || o.kernel >= 10000);
+    k.tma_ty = 8, k.tma_stages = 3, k.tma_minb = 2;
+    if (o.kernel >= 10000) {
+        k.tma_ty = (o.kernel - 10000) / 100;
+        k.tma_stages = (o.kernel / 10) % 10;
+        k.tma_minb = o.kernel % 10;
+    } else if (o.kernel > 0 && o.kernel != 99) {
         const int h = o.kernel / 10, m = o.kernel % 10;
         if (h >= 1 && h <= 3) k.hint = h - 1;
         k.minb = m;
@@ -231,10 +284,61 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
     s.nbx = (s.nxv + tw - 1) / tw;
     s.ngroups = (s.rows + th - 1) / th;
     s.grid = static_cast<unsigned>(s.nbx) * static_cast<unsigned>(s.ngroups);
+    s.grid_b = static_cast<unsigned>(s.nbx) * (s.rows >= 2 ? 2u : 1u);
+    s.use_tma = k.tma && L->tma_kernel && s.rows >= 3;
+    if (s.use_tma) {
+        const int interior = s.rows - 2;
+        s.tma_ntx = (L->p.nx + TMA_TX - 1) / TMA_TX;
+        const long long nty = (interior + L->tma_ty - 1) / L->tma_ty;
+        const long long ntiles = nty * s.tma_ntx;
+        if (ntiles > 0x7fffffffLL) {
+            s.use_tma = false;
+        } else {
+            s.tma_ntiles = static_cast<int>(ntiles);
+            // persistent CTAs: as many as fit on the device at once, never more than tiles
+            long long g = static_cast<long long>(L->tma_resident) * L->sm_count;
+            if (g > ntiles) g = ntiles;
+            s.tma_grid = static_cast<unsigned>(g);
+            s.tma_dq = static_cast<int>(s.tma_grid / s.tma_ntx);
+            s.tma_dr = static_cast<int>(s.tma_grid % s.tma_ntx);
+        }
+    }
+    if (getenv("LBM_DEBUG"))
+        fprintf(stderr, "[lbm] slab rows %d..%d dev %d: %s, grid %u x %d thr, boundary grid %u; tma %d (TY %d, %d stages, %d CTA/SM wanted, %d resident, %zu B smem, grid %u, %d tiles)\n",
+                s.row0, s.row1 - 1, s.device, s.vec4 ? "vec4" : "scalar", s.grid, s.block, s.grid_b, s.use_tma ? 1 : 0, L->tma_ty,
+                L->tma_stages, L->tma_minb, L->tma_resident, L->tma_smem, s.tma_grid, s.tma_ntiles);
     // spread the per-step global atomics over several addresses when there are many CTAs
+    const unsigned ctas = s.use_tma ? s.tma_grid + s.grid_b : s.grid;
     int slots = 1;
-    while (slots < 64 && static_cast<unsigned>(slots) * 1024u < s.grid) slots <<= 1;
+    while (slots < 64 && static_cast<unsigned>(slots) * 1024u < ctas) slots <<= 1;
     s.nslots = slots;
+}
+
+// the lattice as a 3-D tensor (x, y, plane) for the TMA unit; boxes are TMA_TX x TY x 1
+int make_tensor_maps(lbm_lattice* L, Slab& s)
+{
+    static PFN_cuTensorMapEncodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !fn) return fail(LBM_ECUDA, "the driver does not export cuTensorMapEncodeTiled");
+        encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    }
+    const size_t pf = plane_floats(L, s);
+    for (int i = 0; i < 2; i++) {
+        const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(L->p.nx), static_cast<cuuint64_t>(s.rows), Q};
+        const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(L->pitch) * sizeof(float), static_cast<cuuint64_t>(pf) * sizeof(float)};
+        const cuuint32_t estride[3] = {1, 1, 1};
+        for (int w = 0; w < 2; w++) {
+            const cuuint32_t box[3] = {static_cast<cuuint32_t>(w ? TMA_TXW : TMA_TX), static_cast<cuuint32_t>(L->tma_ty), 1};
+            const CUresult r = encode(w ? &s.tmapw[i] : &s.tmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s.lat[i], gdim, gstride, box,
+                                      estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(LBM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+        }
+    }
+    return LBM_OK;
 }
 
 int alloc_slab(lbm_lattice* L, Slab& s, const int* obst_rows_host)
@@ -326,6 +430,7 @@ StepArgs make_args(const lbm_lattice* L, const Slab& s, int src, int step_offset
 {
     StepArgs a;
     memset(&a, 0, sizeof a);
+    a.mode = s.use_tma ? 1 : 0;
     const size_t pf = plane_floats(L, s);
     for (int k = 0; k < Q; k++) {
         a.in[k] = s.lat[src] + k * pf;
@@ -361,26 +466,83 @@ StepArgs make_args(const lbm_lattice* L, const Slab& s, int src, int step_offset
     return a;
 }
 
+TmaArgs make_tma_args(const lbm_lattice* L, const Slab& s, int src, int step_offset)
+{
+    TmaArgs a;
+    memset(&a, 0, sizeof a);
+    const size_t pf = plane_floats(L, s);
+    const float* in = s.lat[src];
+    for (int k = 0; k < Q; k++) a.out[k] = s.lat[src ^ 1] + k * pf;
+    a.west[0] = in + 1 * pf, a.west[1] = in + 5 * pf, a.west[2] = in + 8 * pf;
+    a.east[0] = in + 3 * pf, a.east[1] = in + 6 * pf, a.east[2] = in + 7 * pf;
+    a.obst = s.obst;
+    a.ctrl = s.ctrl;
+    a.sums = s.sums;
+    a.nslots = s.nslots;
+    a.step_offset = step_offset;
+    a.nx = L->p.nx, a.pitch = L->pitch, a.opitch = L->opitch;
+    a.y_first = 1, a.y_end = s.rows - 1;
+    a.ntx = s.tma_ntx, a.ntiles = s.tma_ntiles, a.dq = s.tma_dq, a.dr = s.tma_dr;
+    a.accel_row = s.accel_row;
+    a.omega = L->p.omega, a.w1a = L->w1a, a.w2a = L->w2a;
+    return a;
+}
+
+// one timestep of one slab on its stream, outside a graph: the boundary rows (or every row), then
+// the interior rows
+int launch_step(lbm_lattice* L, Slab& s, int src, int step_offset)
+{
+    const StepArgs a = make_args(L, s, src, step_offset);
+    L->kernel<<<s.use_tma ? s.grid_b : s.grid, s.block, 0, s.stream>>>(a);
+    L->launches++;
+    if (s.use_tma) {
+        const TmaArgs t = make_tma_args(L, s, src, step_offset);
+        L->tma_kernel<<<s.tma_grid, 32 * L->tma_ty + 32, L->tma_smem, s.stream>>>(s.tmap[src], s.tmapw[src], t);
+        L->launches++;
+    }
+    CU(cudaGetLastError());
+    return LBM_OK;
+}
+
 int build_graph(lbm_lattice* L, Slab& s, int parity)
 {
     CU(cudaSetDevice(s.device));
     cudaGraph_t g;
     CU(cudaGraphCreate(&g, 0));
-    cudaGraphNode_t prev = nullptr;
-    std::vector<StepArgs> args(GRAPH_STEPS);
+    // per step: the boundary-row kernel (or the all-row kernel) and, beside it, the interior-row TMA
+    // kernel; both depend on both kernels of the previous step
+    std::vector<cudaGraphNode_t> prev;
     for (int j = 0; j < GRAPH_STEPS; j++) {
-        args[j] = make_args(L, s, (parity + j) & 1, j);
-        void* kp[1] = {&args[j]};
-        cudaKernelNodeParams np;
-        memset(&np, 0, sizeof np);
-        np.func = reinterpret_cast<void*>(L->kernel);
-        np.gridDim = dim3(s.grid, 1, 1);
-        np.blockDim = dim3(s.block, 1, 1);
-        np.sharedMemBytes = 0;
-        np.kernelParams = kp;
-        cudaGraphNode_t node;
-        CU(cudaGraphAddKernelNode(&node, g, prev ? &prev : nullptr, prev ? 1 : 0, &np));
-        prev = node;
+        std::vector<cudaGraphNode_t> cur;
+        const int src = (parity + j) & 1;
+        {
+            StepArgs a = make_args(L, s, src, j);
+            void* kp[1] = {&a};
+            cudaKernelNodeParams np;
+            memset(&np, 0, sizeof np);
+            np.func = reinterpret_cast<void*>(L->kernel);
+            np.gridDim = dim3(s.use_tma ? s.grid_b : s.grid, 1, 1);
+            np.blockDim = dim3(s.block, 1, 1);
+            np.kernelParams = kp;
+            cudaGraphNode_t node;
+            CU(cudaGraphAddKernelNode(&node, g, prev.data(), prev.size(), &np));
+            cur.push_back(node);
+        }
+        if (s.use_tma) {
+            TmaArgs t = make_tma_args(L, s, src, j);
+            void* kp[3] = {&s.tmap[src], &s.tmapw[src], &t};
+            cudaKernelNodeParams np;
+            memset(&np, 0, sizeof np);
+            np.func = reinterpret_cast<void*>(L->tma_kernel);
+            np.gridDim = dim3(s.tma_grid, 1, 1);
+            np.blockDim = dim3(32 * L->tma_ty + 32, 1, 1);
+            np.sharedMemBytes = static_cast<unsigned>(L->tma_smem);
+            np.kernelParams = kp;
+            cudaGraphNode_t node;
+            CU(cudaGraphAddKernelNode(&node, g, prev.data(), prev.size(), &np));
+            cur.push_back(node);
+        }
+        prev = cur;
     }
     {
         int* ctrl = s.ctrl;
@@ -393,7 +555,7 @@ int build_graph(lbm_lattice* L, Slab& s, int parity)
         np.blockDim = dim3(32, 1, 1);
         np.kernelParams = kp;
         cudaGraphNode_t node;
-        CU(cudaGraphAddKernelNode(&node, g, &prev, 1, &np));
+        CU(cudaGraphAddKernelNode(&node, g, prev.data(), prev.size(), &np));
     }
     cudaError_t e = cudaGraphInstantiate(&s.graph[parity], g, 0);
     cudaGraphDestroy(g);
@@ -451,6 +613,30 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
         L->kernel = strict ? vec4_by_hint<true>(k.hint, k.block, k.minb) : vec4_by_hint<false>(k.hint, k.block, k.minb);
     else
         L->kernel = scalar_kernel(strict, k.block);
+    if (k.tma) {
+        TmaChoice c;
+        const bool ok = strict ? tma_by_shape<true>(k.tma_ty, k.tma_stages, k.tma_minb, &c)
+                               : tma_by_shape<false>(k.tma_ty, k.tma_stages, k.tma_minb, &c);
+        if (!ok)
+            return fail(LBM_EINVAL, "no step_tma_kernel variant with %d rows per tile, %d stages, %d CTAs per SM", k.tma_ty,
+                        k.tma_stages, k.tma_minb);
+        L->tma_kernel = c.fn;
+        L->tma_ty = c.ty, L->tma_stages = c.stages, L->tma_minb = c.minb;
+        L->tma_smem = static_cast<size_t>(c.stages) * stage_floats(c.ty) * sizeof(float);
+        // the same kernel runs on every device of the lattice: attributes and occupancy per device
+        for (int i = 0; i < L->nslabs; i++) {
+            CU(cudaSetDevice(L->slabs[i].device));
+            CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(c.fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(L->tma_smem)));
+            int resident = 0, sms = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, reinterpret_cast<const void*>(c.fn), 32 * c.ty + 32,
+                                                             L->tma_smem));
+            CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, L->slabs[i].device));
+            if (resident < 1) return fail(LBM_ECUDA, "step_tma_kernel does not fit on an SM (%zu bytes of shared memory)", L->tma_smem);
+            if (i == 0 || resident < L->tma_resident) L->tma_resident = resident;
+            if (i == 0 || sms < L->sm_count) L->sm_count = sms;
+        }
+    }
     for (int i = 0; i < L->nslabs; i++) slab_geometry(L, L->slabs[i], k);
     return LBM_OK;
 }
@@ -604,6 +790,7 @@ static int create_common(const lbm_param_t* params, const lbm_options_t* opt, in
     for (int i = 0; i < nslabs && !rc; i++) {
         Slab& s = L->slabs[i];
         rc = alloc_slab(L, s, obstacles + static_cast<size_t>(s.row0 - starts[0]) * params->nx);
+        if (!rc && s.use_tma) rc = make_tensor_maps(L, s);
         if (!rc && uses_halo(L)) rc = alloc_halo(L, s);
     }
     if (rc) {
@@ -841,7 +1028,7 @@ int lbm_run(lbm_lattice_t* L, int iters)
                 }
                 CU(cudaSetDevice(s.device));
                 CU(cudaGraphLaunch(s.graph[parity], s.stream));
-                L->launches += GRAPH_STEPS + 1;
+                L->launches += GRAPH_STEPS * (s.use_tma ? 2 : 1) + 1;
             }
             done += GRAPH_STEPS;
         }
@@ -851,9 +1038,8 @@ int lbm_run(lbm_lattice_t* L, int iters)
         for (int i = 0; i < L->nslabs; i++) {
             Slab& s = L->slabs[i];
             CU(cudaSetDevice(s.device));
-            const StepArgs a = make_args(L, s, (parity + j) & 1, j);
-            L->kernel<<<s.grid, s.block, 0, s.stream>>>(a);
-            L->launches++;
+            int rc = launch_step(L, s, (parity + j) & 1, j);
+            if (rc) return rc;
         }
     }
     for (int i = 0; i < L->nslabs; i++) {
@@ -1121,6 +1307,25 @@ int lbm_last_run_ms(lbm_lattice_t* L, float* ms)
 }
 
 long long lbm_kernel_launches(const lbm_lattice_t* L) { return L ? L->launches : 0; }
+
+int lbm_selftest(int device, unsigned long long pairs, unsigned long long seed, unsigned long long* mismatches)
+{
+    if (!mismatches) return fail(LBM_EINVAL, "NULL argument");
+    int rc = check_device_available();
+    if (rc) return rc;
+    CU(cudaSetDevice(device));
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    CU(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+    const unsigned blocks = 148 * 8, threads = 256;
+    const unsigned long long per_thread = (pairs + static_cast<unsigned long long>(blocks) * threads - 1) / (static_cast<unsigned long long>(blocks) * threads);
+    selftest_kernel<<<blocks, threads>>>(per_thread, seed, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(mismatches, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(LBM_ECUDA, "self-test kernel failed: %s", cudaGetErrorString(e));
+    return LBM_OK;
+}
 
 int lbm_num_slabs(const lbm_lattice_t* L) { return L ? L->nslabs : 0; }
 

