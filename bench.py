@@ -349,7 +349,7 @@ def main() -> int:
                        kernel=args.kernel, block=args.block),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": BYTES_PER_LUP * cells / n, "kernel": "lbm::step_vec4_kernel",
+                     "algorithmic_bytes_per_launch": BYTES_PER_LUP * cells / n, "kernel": "lbm::step_tma_kernel",
                      "per_gpu": True},
         "gpu_launches": launches,
         "clocks": clocks,

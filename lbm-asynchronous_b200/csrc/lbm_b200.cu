@@ -596,6 +596,14 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
         return fail(LBM_EINVAL, "halo_lag is only meaningful with LBM_HALO_SYNC");
     L->pitch = (params->nx + 31) / 32 * 32;
     L->opitch = L->pitch / 32;
+    // Ring depth.  Slots are labelled by d = (producer step + 1): the consumer's step s reads d = s - lag,
+    // the producer's step t writes d = t + 1.  In sync mode the consumer of step s waits until the
+    // producer has finished step s-lag-1, and symmetrically the producer (a consumer in the other
+    // direction) cannot start step t before its neighbour finished step t-lag-1.  So while the producer
+    // writes d = t+1 the neighbour is reading some d' in [t-2*lag, t+1], and d' = t+1 is only read after
+    // the write was signalled: no slot is overwritten while live iff ring > (t+1) - (t-2*lag), i.e.
+    // ring >= 2*lag + 2.  (Async mode: lag = 0, ring = 2 -- the A/B parity buffers of the reference,
+    // SURVEY.md App. C-3; races there are the mode's definition.)
     L->ring = 2 * L->opt.halo_lag + 2;
     // exactly the reference's expressions (float arithmetic, left to right)
     L->w0 = params->density * 4.f / 9.f;  // SerialCode:546

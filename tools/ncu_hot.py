@@ -9,8 +9,12 @@ ia, isrc, iex, ismp = hdr.index("Address"), hdr.index("Source"), hdr.index("Inst
 ops = collections.Counter()
 tot = 0
 hot = []
-for r in rows[2:]:
-    if len(r) <= iex:
+kernels_seen = 0
+for r in rows[1:]:
+    if r and r[0] == "Address":
+        kernels_seen += 1  # a report with several launches repeats the header: keep the first launch only
+        continue
+    if kernels_seen > 1 or len(r) <= iex:
         continue
     src = r[isrc].strip()
     m = re.match(r"(?:@!?U?P\w+\s+)?([A-Z][A-Z0-9_]*)", src)
