@@ -312,8 +312,13 @@ def main() -> int:
         else:
             sh2 = ShardedLattice(param, lambda a, b: obst_pinned.numpy(), local_rank, **opts)
             lat2, run2 = sh2.slab, sh2
+        lat2.sync()
+        t1 = time.perf_counter()
         run2.run(K)
+        lat2.sync()
+        t2 = time.perf_counter()
         av2 = run2.av_vels()
+        t3 = time.perf_counter()
         import ctypes as C
 
         from lbm_asynchronous_b200.capi import check, library
@@ -322,13 +327,14 @@ def main() -> int:
         torch.cuda.synchronize()
         barrier()
         secs = time.perf_counter() - t0
+        phases = {"create_upload": t1 - t0, "run": t2 - t1, "av_vels": t3 - t2, "final_state_download": t0 + secs - t3}
         if dist is not None:
             t = torch.tensor([secs], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             secs = float(t.item())
         e2e = {"value": cells * K / secs / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": my_cells * 4 * n / K, "d2h_bytes_per_step": (my_cells * 16 * n + K * 8 * 3) / K,
-               "seconds": secs, "what": "lbm_create(host obstacles) + lbm_run(K) + lbm_av_vels + lbm_final_state to pinned host"}
+               "seconds": secs, "phases_s_rank0": phases, "what": "lbm_create(host obstacles) + lbm_run(K) + lbm_av_vels + lbm_final_state to pinned host"}
         if n == 1:
             lat2.close()
         else:

@@ -132,6 +132,7 @@ struct lbm_lattice {
     void (*kernel)(StepArgs) = nullptr;                 // all rows, or the boundary rows next to step_tma_kernel
     void (*tma_kernel)(CUtensorMap, CUtensorMap, TmaArgs) = nullptr; // interior rows (null: `kernel` does every row)
     int tma_ty = 0, tma_stages = 0, tma_minb = 0, tma_resident = 0, sm_count = 0;
+    int prio_high = 0; // numerically lowest = most urgent stream / kernel-node priority of the device
     size_t tma_smem = 0;
 };
 
@@ -526,6 +527,14 @@ int build_graph(lbm_lattice* L, Slab& s, int parity)
             np.kernelParams = kp;
             cudaGraphNode_t node;
             CU(cudaGraphAddKernelNode(&node, g, prev.data(), prev.size(), &np));
+            if (s.use_tma) {
+                // the few boundary CTAs must not queue behind the persistent interior kernel (which fills
+                // every SM): their halo rows and flags are what the neighbour GPU's next step waits for
+                cudaKernelNodeAttrValue v;
+                memset(&v, 0, sizeof v);
+                v.priority = L->prio_high;
+                CU(cudaGraphKernelNodeSetAttribute(node, cudaKernelNodeAttributePriority, &v));
+            }
             cur.push_back(node);
         }
         if (s.use_tma) {
@@ -614,6 +623,11 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
     if (const char* t = getenv("LBM_HALO_TIMEOUT_MS")) {
         const long long ms = atoll(t);
         if (ms > 0) L->timeout_ns = static_cast<unsigned long long>(ms) * 1000000ull;
+    }
+    {
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess) L->prio_high = hi;
+        cudaGetLastError();
     }
     const KernelChoice k = choose_kernel(L->opt, params->nx);
     const bool strict = L->opt.arith == LBM_ARITH_STRICT;
