@@ -194,7 +194,7 @@ bool tma_by_shape(int ty, int stages, int minb, TmaChoice* c)
 }
 
 // opt.kernel:
-//   0            library default: step_tma_kernel (TY 8, 3 stages) for the interior rows when nx % 4 == 0,
+//   0            library default: step_tma_kernel (TY 16, 2 stages, 1 CTA/SM) for the interior rows when nx % 4 == 0,
 //                nx >= 128 and the slab has >= 3 rows, step_vec4_kernel / step_scalar_kernel otherwise
 //   1TTSM        step_tma_kernel with TT rows per tile, S stages, M resident CTAs per SM asked of the compiler
 //                (10823 10822 10832 10831 10841 10434 10444 10443 10462 11621 11631)
@@ -214,7 +214,7 @@ KernelChoice choose_kernel(const lbm_options_t& o, int nx)
     k.minb = 1;
     k.block = (o.block == 128 || o.block == 256 || o.block == 512) ? o.block : 256;
     k.tma = k.vec4 && nx >= TMA_TX && (o.kernel == 0 || o.kernel >= 10000);
-    k.tma_ty = 8, k.tma_stages = 3, k.tma_minb = 2;
+    k.tma_ty = 16, k.tma_stages = 2, k.tma_minb = 1; // best of the r01 sweep on 8192^2 and 32768x4096 (profiles/)
     if (o.kernel >= 10000) {
         k.tma_ty = (o.kernel - 10000) / 100;
         k.tma_stages = (o.kernel / 10) % 10;
