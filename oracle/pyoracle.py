@@ -17,6 +17,12 @@ import subprocess
 
 import numpy as np
 
+# libgomp reads its environment when it is first loaded.  Without a binding policy the threads of the
+# oracle's OpenMP loops were observed to share ONE core in the build container (8 threads, 1x speed);
+# the reference's own env.sh binds threads as well (OpenMP/env.sh:2-4).
+os.environ.setdefault("OMP_PROC_BIND", "spread")
+os.environ.setdefault("OMP_PLACES", "cores")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liblbm_oracle.so")
 NSPEEDS = 9
