@@ -113,27 +113,25 @@ class ClockSampler(threading.Thread):
 # the reference's CPU implementation (oracle/_ref: the reference's own OpenMP program, built from
 # /root/reference by oracle/Makefile) on a bounded sample of the workload
 # -------------------------------------------------------------------------------------------------
-def run_reference_cpu(nx: int, rows: int, iters: int, threads: int | None = None):
-    """Runs oracle/_ref/d2q9-bgk-openmp on an nx x rows channel of the benchmark's generator for `iters`
-    steps; returns (MLUPS from the program's own 'Elapsed Compute time', seconds, kind).  Falls back to the
-    oracle's fused port when the prebuilt reference binary is absent."""
+def run_reference_cpu(nx: int, rows: int, iters: int, threads: int | None = None, program: str = "openmp"):
+    """Runs a prebuilt reference program (oracle/_ref: the reference's own sources compiled by oracle/Makefile;
+    the MPI programs over oracle/minimpi with one rank per core) on an nx x rows channel of the benchmark's
+    generator for `iters` steps; returns (MLUPS from the program's own 'Elapsed Compute time', seconds, kind).
+    Falls back to the oracle's fused port when the prebuilt binary is absent."""
     threads = threads or os.cpu_count() or 1
-    exe = os.path.join(ROOT, "oracle", "_ref", "d2q9-bgk-openmp")
+    orc = entry.load_oracle()
     gen = os.path.join(ROOT, "lbm-asynchronous_b200", "gen_channel")
-    if os.path.exists(exe) and os.path.exists(gen):
+    if orc.reference_binary(program) and os.path.exists(gen):
         td = tempfile.mkdtemp(prefix="lbm_ref_")
         try:
             subprocess.run([gen, str(nx), str(rows), str(iters), "in.params", "in.obstacles"], cwd=td, check=True)
-            # the reference always writes final_state.dat (87 B of text per cell): send it to /dev/null
-            os.symlink("/dev/null", os.path.join(td, "final_state.dat"))
-            env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="true", OMP_PLACES="cores")  # OpenMP/env.sh:2-4
-            r = subprocess.run([exe, "in.params", "in.obstacles"], cwd=td, env=env, capture_output=True, text=True, check=True)
-            m = re.search(r"Elapsed Compute time:\s+([0-9.]+)", r.stdout)
-            secs = float(m.group(1))
+            mpi = program != "openmp" and program != "serial"
+            nranks = min(threads, max(1, (rows - 3))) if mpi else 1
+            secs = orc.run_reference(program, os.path.join(td, "in.params"), os.path.join(td, "in.obstacles"), td, nranks=nranks,
+                                     threads=None if mpi else threads, discard_final_state=True)
             return nx * rows * iters / secs / 1e6, secs, "reference"
         finally:
             shutil.rmtree(td, ignore_errors=True)
-    orc = entry.load_oracle()
     pkg = entry.load_package()
     os.environ.setdefault("OMP_NUM_THREADS", str(threads))
     p = orc.Params(nx, rows, iters, 10, 0.1, 0.005, 1.85)
@@ -157,8 +155,17 @@ def reference_arm(args) -> int:
     rows = int(4.0e9 / (nx * max(total_steps, 1)))
     rows = max(64, min(2048, rows // 64 * 64))
     run_reference_cpu(nx, rows, max(args.warmup, 1), cores)  # warm-up run (page cache, CPU clocks)
-    mlups, secs, kind = run_reference_cpu(nx, rows, args.steps, cores)
-    sample = f"{nx}x{rows} rows of the channel workload, {args.steps} steps, {cores} OpenMP threads"
+    # every maintained variant of the reference on the same sample; the arm's value is the fastest one
+    results = {}
+    for prog in ("openmp", "MPI_Waitall", "MPI_Testall_OptimizedVersion", "MPI"):
+        try:
+            results[prog] = run_reference_cpu(nx, rows, args.steps, cores, program=prog)
+        except Exception as ex:
+            print(f"bench.py: reference program {prog} failed: {ex}", file=sys.stderr)
+    best = max(results, key=lambda k: results[k][0])
+    mlups, secs, kind = results[best]
+    sample = (f"{nx}x{rows} rows of the channel workload, {args.steps} steps, {cores} host threads/ranks; fastest reference "
+              f"program = {best}; all: " + ", ".join(f"{k} {v[0]:.0f}" for k, v in results.items()) + " MLUPS")
     line = {
         "impl": "reference", "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -368,6 +375,16 @@ def main() -> int:
             v, secs, kind = run_reference_cpu(nx, rows, iters, cores)
             line["cpu_baseline"] = {"value": v, "unit": "MLUPS", "cores": cores, "kind": kind, "seconds": secs,
                                     "sample": f"{nx}x{rows} rows of the same channel workload, {iters} steps, OpenMP program of the reference"}
+            # the reference's MPI programs on the same sample, one rank per core over oracle/minimpi (reported beside it)
+            others = {}
+            for prog in ("MPI", "MPI_Waitall", "MPI_Testall_OptimizedVersion"):
+                try:
+                    mv, ms_, mk = run_reference_cpu(nx, rows, iters, cores, program=prog)
+                    if mk == "reference":
+                        others[prog] = round(mv, 1)
+                except Exception as ex:
+                    others[prog] = f"failed: {str(ex)[:80]}"
+            line["cpu_baseline"]["mpi_programs_mlups"] = others
         except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
             line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": cores, "kind": "reference", "sample": f"failed: {ex}"}
     print(json.dumps(line), flush=True)

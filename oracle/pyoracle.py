@@ -262,3 +262,52 @@ def run_decomposed(p: Params, obstacles: np.ndarray, starts, halo_lag: int, iter
     if rc != 0:
         raise ValueError(f"oracle_run_decomposed rejected its arguments (rc={rc})")
     return cells, av
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own programs (oracle/_ref, built by oracle/Makefile from /root/reference)
+# ---------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(_HERE, "_ref")
+
+
+def reference_binary(name: str) -> str | None:
+    """Path of a prebuilt reference program (serial, openmp, MPI, MPI_Waitall,
+    MPI_Testall_OptimizedVersion, each MPI one also with the suffix -strict), or None."""
+    path = os.path.join(REF_DIR, "d2q9-bgk-" + name)
+    return path if os.path.exists(path) else None
+
+
+def run_reference(name: str, params_file: str, obstacles_file: str, workdir: str, nranks: int = 1, threads: int | None = None,
+                  eager_bytes: int | None = None, discard_final_state: bool = False, timeout: float = 3600.0):
+    """Run a reference program in `workdir` (it writes av_vels.dat / final_state.dat there).  MPI programs
+    run over oracle/minimpi with `nranks` ranks.  Returns the program's own 'Elapsed Compute time' (s)."""
+    import re
+    import resource
+
+    exe = reference_binary(name)
+    if exe is None:
+        raise FileNotFoundError(f"oracle/_ref/d2q9-bgk-{name} is not built (run `make -C oracle ref` where /root/reference is mounted)")
+    os.makedirs(workdir, exist_ok=True)
+    if discard_final_state:  # 87 bytes of text per cell: send it to /dev/null for timing runs
+        fs = os.path.join(workdir, "final_state.dat")
+        if os.path.lexists(fs):
+            os.remove(fs)
+        os.symlink("/dev/null", fs)
+    env = dict(os.environ, MINIMPI_NP=str(nranks))
+    if threads:
+        env.update(OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="true", OMP_PLACES="cores")  # OpenMP/env.sh:2-4
+    if eager_bytes:
+        env["MINIMPI_EAGER_BYTES"] = str(eager_bytes)
+
+    def unlimited_stack():  # the MPI variants keep row-sized VLAs on the stack (MPI/d2q9-bgk.c:298,816)
+        try:
+            resource.setrlimit(resource.RLIMIT_STACK, (resource.RLIM_INFINITY, resource.RLIM_INFINITY))
+        except (ValueError, OSError):
+            pass
+
+    r = subprocess.run([exe, params_file, obstacles_file], cwd=workdir, env=env, capture_output=True, text=True, timeout=timeout,
+                       preexec_fn=unlimited_stack)
+    if r.returncode != 0:
+        raise RuntimeError(f"{name} failed ({r.returncode}): {r.stdout[-500:]} {r.stderr[-500:]}")
+    m = re.search(r"Elapsed Compute time:\s+([0-9.]+)", r.stdout)
+    return float(m.group(1))
