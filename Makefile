@@ -25,7 +25,7 @@ $(LIB): $(wildcard $(PKG)/csrc/*.cu $(PKG)/csrc/*.cuh) include/lbm_b200.h
 
 $(BIN): $(PKG)/host/d2q9-bgk.c include/lbm_b200.h $(LIB)
 	$(HOSTCC) -std=c99 -O2 -Wall -Wextra -D_POSIX_C_SOURCE=200809L -Iinclude $(PKG)/host/d2q9-bgk.c -o $@ \
-	    -L$(PKG) -llbm_b200 -Wl,-rpath,'$$ORIGIN' -lm
+	    -L$(PKG) -llbm_b200 -Wl,-rpath,'$$ORIGIN' -lm -lpthread
 
 $(PKG)/gen_channel: $(PKG)/host/gen_channel.c
 	$(HOSTCC) -std=c99 -O2 -Wall -Wextra $< -o $@

@@ -74,7 +74,8 @@ typedef struct {
     int halo_mode;   /* LBM_HALO_*             default LBM_HALO_SYNC */
     int halo_lag;    /* LBM_HALO_SYNC only: boundary rows at step t use the neighbour row of step
                         t-halo_lag (even, >= 0; 0 = exact).  The deterministic stale-halo mode. */
-    int use_graph;   /* 1: replay the step loop from CUDA graphs (default), 0: one launch per step */
+    int use_graph;   /* 1: keep the step loop on the device (default): one cooperative launch per run for grids
+                        that live in L2, CUDA graphs of 32 steps otherwise; 0: one plain launch per step */
     int kernel;      /* kernel variant, 0 = library default; for tuning/bench only */
     int block;       /* threads per CTA, 0 = default */
 } lbm_options_t;

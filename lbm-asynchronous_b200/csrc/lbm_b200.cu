@@ -19,6 +19,7 @@
 #include <cudaTypedefs.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -101,6 +102,11 @@ struct Slab {
     unsigned grid_b = 0;  // boundary rows only (mode 1)
     bool vec4 = false;
     int accel_row = -1;
+    // whole runs in one cooperative launch (step_loop_kernel), L2-resident single-slab grids
+    bool use_loop = false;
+    unsigned loop_grid = 0;
+    int loop_vec = 4, loop_block = 256, loop_tw_shift = 0, loop_nbx = 0, loop_nxv = 0, loop_ntiles = 0;
+    unsigned* loop_barrier = nullptr;
     // interior rows through step_tma_kernel
     bool use_tma = false;
     CUtensorMap tmap[2];  // per lattice: boxes TMA_TX wide
@@ -130,8 +136,10 @@ struct lbm_lattice {
     float w1a = 0, w2a = 0;         // accelerate_flow weights, SerialCode:222-223
     unsigned long long timeout_ns = 30ull * 1000000000ull;
     void (*kernel)(StepArgs) = nullptr;                 // all rows, or the boundary rows next to step_tma_kernel
+    void (*loop_kernel[2])(LoopArgs) = {nullptr, nullptr}; // step_loop_kernel: [0] 1 cell per thread, [1] 4 cells
     void (*tma_kernel)(CUtensorMap, CUtensorMap, TmaArgs) = nullptr; // interior rows (null: `kernel` does every row)
     int tma_ty = 0, tma_stages = 0, tma_minb = 0, tma_resident = 0, sm_count = 0;
+    int loop_resident[2] = {0, 0};
     int prio_high = 0; // numerically lowest = most urgent stream / kernel-node priority of the device
     size_t tma_smem = 0;
 };
@@ -200,7 +208,13 @@ bool tma_by_shape(int ty, int stages, int minb, TmaChoice* c)
 //                (10823 10822 10832 10831 10841 10434 10444 10443 10462 11621 11631)
 //   H M (10..39) step_vec4_kernel for every row: hint = H-1 (0 plain, 1 ld.nc.no_allocate, 2 + st.cs), min blocks M
 //   99           step_scalar_kernel for every row
+//   200          step_loop_kernel (all steps of a run in one cooperative launch); also the default for
+//                single-slab grids whose two lattices fit in L2 (<= LOOP_MAX_CELLS cells).  201 / 204 force
+//                its 1-cell / 4-cell per thread mapping (default: 1 cell below LOOP_VEC4_CELLS cells)
+constexpr long long LOOP_MAX_CELLS = 1400000; // 2 x 36 B x cells <= ~100 MB of the 126 MB L2
+constexpr long long LOOP_VEC4_CELLS = 300000; // below this a grid cannot fill the SMs with 4 cells per thread
 struct KernelChoice {
+    bool loop;
     bool vec4;
     int hint, block, minb;
     bool tma;
@@ -210,16 +224,17 @@ KernelChoice choose_kernel(const lbm_options_t& o, int nx)
 {
     KernelChoice k;
     k.vec4 = (nx % 4 == 0) && o.kernel != 99;
+    k.loop = (o.kernel == 0 || o.kernel == 200 || o.kernel == 201 || o.kernel == 204);
     k.hint = 0;
     k.minb = 1;
     k.block = (o.block == 128 || o.block == 256 || o.block == 512) ? o.block : 256;
-    k.tma = k.vec4 && nx >= TMA_TX && (o.kernel == 0 || o.kernel >= 10000);
+    k.tma = k.vec4 && nx >= TMA_TX && (o.kernel == 0 || (o.kernel >= 200 && o.kernel <= 204) || o.kernel >= 10000);
     k.tma_ty = 16, k.tma_stages = 2, k.tma_minb = 1; // best of the r01 sweep on 8192^2 and 32768x4096 (profiles/)
     if (o.kernel >= 10000) {
         k.tma_ty = (o.kernel - 10000) / 100;
         k.tma_stages = (o.kernel / 10) % 10;
         k.tma_minb = o.kernel % 10;
-    } else if (o.kernel > 0 && o.kernel != 99) {
+    } else if (o.kernel > 0 && o.kernel < 99) {
         const int h = o.kernel / 10, m = o.kernel % 10;
         if (h >= 1 && h <= 3) k.hint = h - 1;
         k.minb = m;
@@ -271,6 +286,7 @@ int validate_params(const lbm_param_t* p)
 }
 
 size_t plane_floats(const lbm_lattice* L, const Slab& s) { return static_cast<size_t>(s.rows) * L->pitch; }
+bool uses_halo_cfg(const lbm_lattice* L) { return L->per_process || L->nslabs > 1; }
 
 void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
 {
@@ -286,7 +302,33 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
     s.ngroups = (s.rows + th - 1) / th;
     s.grid = static_cast<unsigned>(s.nbx) * static_cast<unsigned>(s.ngroups);
     s.grid_b = static_cast<unsigned>(s.nbx) * (s.rows >= 2 ? 2u : 1u);
-    s.use_tma = k.tma && L->tma_kernel && s.rows >= 3;
+    // step loop: single slab without halos; tiles strided over the CTAs that are resident at once
+    s.use_loop = false;
+    if (k.loop && L->opt.use_graph && !uses_halo_cfg(L) &&
+        (L->opt.kernel >= 200 || static_cast<long long>(L->p.nx) * s.rows <= LOOP_MAX_CELLS)) {
+        const long long cells = static_cast<long long>(L->p.nx) * s.rows;
+        bool v4 = k.vec4 && cells >= LOOP_VEC4_CELLS;
+        if (L->opt.kernel == 201) v4 = false;
+        if (L->opt.kernel == 204) v4 = k.vec4;
+        s.loop_vec = v4 ? 4 : 1;
+        s.loop_block = v4 ? 256 : 128;
+        s.loop_nxv = v4 ? L->p.nx / 4 : L->p.nx;
+        int lsh = next_pow2_shift(s.loop_nxv);
+        const int lbsh = next_pow2_shift(s.loop_block);
+        if (lsh > lbsh) lsh = lbsh;
+        s.loop_tw_shift = lsh;
+        const int ltw = 1 << lsh, lth = s.loop_block >> lsh;
+        s.loop_nbx = (s.loop_nxv + ltw - 1) / ltw;
+        const long long ntiles = static_cast<long long>(s.loop_nbx) * ((s.rows + lth - 1) / lth);
+        long long g = static_cast<long long>(L->loop_resident[v4 ? 1 : 0]) * L->sm_count;
+        if (g > ntiles) g = ntiles;
+        if (g >= 1 && ntiles <= 0x7fffffffLL && L->loop_kernel[v4 ? 1 : 0]) {
+            s.loop_ntiles = static_cast<int>(ntiles);
+            s.loop_grid = static_cast<unsigned>(g);
+            s.use_loop = true;
+        }
+    }
+    s.use_tma = !s.use_loop && k.tma && L->tma_kernel && s.rows >= 3;
     if (s.use_tma) {
         const int interior = s.rows - 2;
         s.tma_ntx = (L->p.nx + TMA_TX - 1) / TMA_TX;
@@ -305,8 +347,9 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
         }
     }
     if (getenv("LBM_DEBUG"))
-        fprintf(stderr, "[lbm] slab rows %d..%d dev %d: %s, grid %u x %d thr, boundary grid %u; tma %d (TY %d, %d stages, %d CTA/SM wanted, %d resident, %zu B smem, grid %u, %d tiles)\n",
-                s.row0, s.row1 - 1, s.device, s.vec4 ? "vec4" : "scalar", s.grid, s.block, s.grid_b, s.use_tma ? 1 : 0, L->tma_ty,
+        fprintf(stderr, "[lbm] slab rows %d..%d dev %d: %s, grid %u x %d thr, boundary grid %u; loop %d (%d cell/thread, grid %u, %d tiles); tma %d (TY %d, %d stages, %d CTA/SM wanted, %d resident, %zu B smem, grid %u, %d tiles)\n",
+                s.row0, s.row1 - 1, s.device, s.vec4 ? "vec4" : "scalar", s.grid, s.block, s.grid_b, s.use_loop ? 1 : 0, s.loop_vec, s.loop_grid,
+                s.loop_ntiles, s.use_tma ? 1 : 0, L->tma_ty,
                 L->tma_stages, L->tma_minb, L->tma_resident, L->tma_smem, s.tma_grid, s.tma_ntiles);
     // spread the per-step global atomics over several addresses when there are many CTAs
     const unsigned ctas = s.use_tma ? s.tma_grid + s.grid_b : s.grid;
@@ -360,6 +403,7 @@ int alloc_slab(lbm_lattice* L, Slab& s, const int* obst_rows_host)
     CU(cudaMalloc(&s.error, sizeof(int)));
     CU(cudaMemsetAsync(s.error, 0, sizeof(int), s.stream));
     CU(cudaMalloc(&s.state_sums, (SUM_WORDS + 1) * sizeof(unsigned long long)));
+    CU(cudaMalloc(&s.loop_barrier, 128));
 
     // initial state: every cell, obstacles included (SerialCode:551-567); both lattices
     const float w[Q] = {L->w0, L->w1, L->w1, L->w1, L->w1, L->w2, L->w2, L->w2, L->w2};
@@ -635,6 +679,22 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
         L->kernel = strict ? vec4_by_hint<true>(k.hint, k.block, k.minb) : vec4_by_hint<false>(k.hint, k.block, k.minb);
     else
         L->kernel = scalar_kernel(strict, k.block);
+    if (k.loop && !uses_halo_cfg(L)) {
+        L->loop_kernel[0] = strict ? step_loop_kernel<true, 128, 1> : step_loop_kernel<false, 128, 1>;
+        L->loop_kernel[1] = strict ? step_loop_kernel<true, 256, 4> : step_loop_kernel<false, 256, 4>;
+        CU(cudaSetDevice(L->slabs[0].device));
+        int sms = 0, coop = 0;
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, L->slabs[0].device));
+        CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, L->slabs[0].device));
+        L->sm_count = sms;
+        for (int v = 0; v < 2; v++) {
+            int resident = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, reinterpret_cast<const void*>(L->loop_kernel[v]),
+                                                             v ? 256 : 128, 0));
+            L->loop_resident[v] = coop ? resident : 0;
+            if (!coop) L->loop_kernel[v] = nullptr;
+        }
+    }
     if (k.tma) {
         TmaChoice c;
         const bool ok = strict ? tma_by_shape<true>(k.tma_ty, k.tma_stages, k.tma_minb, &c)
@@ -677,6 +737,7 @@ void free_slab(Slab& s)
     cudaFree(s.error);
     cudaFree(s.sums);
     cudaFree(s.state_sums);
+    cudaFree(s.loop_barrier);
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
@@ -1040,6 +1101,36 @@ int lbm_run(lbm_lattice_t* L, int iters)
     }
     int done = 0;
     const int parity = L->cur;
+    if (L->nslabs == 1 && L->slabs[0].use_loop) {
+        // every step of this run in cooperative launches of step_loop_kernel (one, unless the barrier
+        // counter of 32 bits would overflow)
+        Slab& s = L->slabs[0];
+        CU(cudaSetDevice(s.device));
+        const long long max_steps = 0xffffffffLL / s.loop_grid - 1;
+        while (done < iters) {
+            const int n = static_cast<int>(std::min<long long>(iters - done, max_steps));
+            LoopArgs a;
+            memset(&a, 0, sizeof a);
+            a.lat[0] = s.lat[0], a.lat[1] = s.lat[1];
+            a.pf = plane_floats(L, s);
+            a.obst = s.obst;
+            a.sums = s.sums + static_cast<size_t>(done) * s.nslots * SUM_WORDS;
+            a.barrier = s.loop_barrier;
+            a.nslots = s.nslots;
+            a.first_step = first + done, a.nsteps = n, a.last_step = first + iters - 1;
+            a.src = (parity + done) & 1;
+            a.nx = L->p.nx, a.nxv = s.loop_nxv, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
+            a.tw_shift = s.loop_tw_shift, a.nbx = s.loop_nbx, a.ntiles = s.loop_ntiles;
+            a.accel_row = s.accel_row;
+            a.omega = L->p.omega, a.w1a = L->w1a, a.w2a = L->w2a;
+            CU(cudaMemsetAsync(s.loop_barrier, 0, sizeof(unsigned), s.stream));
+            void* kp[1] = {&a};
+            CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(L->loop_kernel[s.loop_vec == 4 ? 1 : 0]), dim3(s.loop_grid),
+                                           dim3(s.loop_block), kp, 0, s.stream));
+            L->launches++;
+            done += n;
+        }
+    }
     if (L->opt.use_graph && !L->interleaved) {
         while (iters - done >= GRAPH_STEPS) {
             for (int i = 0; i < L->nslabs; i++) {

@@ -21,10 +21,12 @@
  *   LBM_SKIP_FINAL_STATE=1   do not write final_state.dat (87 bytes per cell of text)
  *   LBM_KERNEL, LBM_BLOCK    kernel variant / CTA size (tuning)
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/time.h>
+#include <unistd.h>
 
 #include "lbm_b200.h"
 
@@ -117,19 +119,80 @@ static int* read_obstacles(const char* path, const lbm_param_t* p)
 }
 
 /* final_state.dat: `ii jj u_x u_y u pressure obstacle`, jj outer / ii inner (SerialCode:679-724);
- * av_vels.dat: `tt:\tvalue` (:735-738) */
+ * av_vels.dat: `tt:\tvalue` (:735-738).
+ * The reference formats 87 bytes per cell with one fprintf per cell on one core -- at 1024 x 1024 that
+ * is 91 MB of text and takes far longer than the simulation.  Same bytes here, but the rows are
+ * formatted by all host cores (snprintf into per-band buffers) and written in order. */
+typedef struct {
+    const lbm_param_t* p;
+    const int* obstacles;
+    const float *ux, *uy, *u, *pressure;
+    int row0, row1;
+    char* buf;
+    size_t len;
+    int failed;
+} format_job;
+
+static void* format_rows(void* arg)
+{
+    format_job* j = (format_job*)arg;
+    const int nx = j->p->nx;
+    const size_t cap = (size_t)(j->row1 - j->row0) * (size_t)nx * 112 + 16; /* a line is at most 2*11+4*20+1+7 bytes */
+    j->buf = malloc(cap);
+    if (!j->buf) {
+        j->failed = 1;
+        return NULL;
+    }
+    size_t at = 0;
+    for (int jj = j->row0; jj < j->row1; jj++)
+        for (int ii = 0; ii < nx; ii++) {
+            const size_t c = (size_t)ii + (size_t)jj * nx;
+            at += (size_t)snprintf(j->buf + at, cap - at, "%d %d %.12E %.12E %.12E %.12E %d\n", ii, jj, j->ux[c], j->uy[c], j->u[c],
+                                   j->pressure[c], j->obstacles[c]);
+        }
+    j->len = at;
+    return NULL;
+}
+
 static void write_final_state(const lbm_param_t* p, const int* obstacles, const float* ux, const float* uy, const float* u,
                               const float* pressure)
 {
     FILE* fp = fopen(FINAL_STATE_FILE, "w");
     if (!fp) DIE("could not open file output file");
-    static char buf[1 << 20];
-    setvbuf(fp, buf, _IOFBF, sizeof buf);
-    for (int jj = 0; jj < p->ny; jj++)
-        for (int ii = 0; ii < p->nx; ii++) {
-            const size_t c = (size_t)ii + (size_t)jj * p->nx;
-            fprintf(fp, "%d %d %.12E %.12E %.12E %.12E %d\n", ii, jj, ux[c], uy[c], u[c], pressure[c], obstacles[c]);
+    long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+    int nthreads = (int)(ncpu < 1 ? 1 : (ncpu > 64 ? 64 : ncpu));
+    /* one band of rows per thread and round; at most ~1 M cells per band keeps the text buffers bounded
+     * (112 MB each) */
+    const size_t cells_per_band = 1u << 20;
+    int band_rows = (int)(cells_per_band / (size_t)p->nx);
+    const int even_rows = (p->ny + nthreads - 1) / nthreads;
+    if (band_rows > even_rows) band_rows = even_rows;
+    if (band_rows < 1) band_rows = 1;
+    format_job* jobs = calloc((size_t)nthreads, sizeof *jobs);
+    pthread_t* tids = calloc((size_t)nthreads, sizeof *tids);
+    if (!jobs || !tids) DIE("cannot allocate memory for the output threads");
+    int row = 0;
+    while (row < p->ny) {
+        int n = 0;
+        for (; n < nthreads && row < p->ny; n++) {
+            const int r1 = row + band_rows < p->ny ? row + band_rows : p->ny;
+            format_job j = {p, obstacles, ux, uy, u, pressure, row, r1, NULL, 0, 0};
+            jobs[n] = j;
+            row = r1;
+            if (pthread_create(&tids[n], NULL, format_rows, &jobs[n]) != 0) {
+                format_rows(&jobs[n]); /* no thread: format here */
+                tids[n] = 0;
+            }
         }
+        for (int i = 0; i < n; i++) {
+            if (tids[i]) pthread_join(tids[i], NULL);
+            if (jobs[i].failed) DIE("cannot allocate memory for the output buffers");
+            if (fwrite(jobs[i].buf, 1, jobs[i].len, fp) != jobs[i].len) DIE("could not write file output file");
+            free(jobs[i].buf);
+        }
+    }
+    free(jobs);
+    free(tids);
     fclose(fp);
 }
 

@@ -79,6 +79,8 @@ def exact_tot_u(orc, p, obst, cells_before, k):
     (128, 128, 10832, 0), (128, 3, 10832, 0), (128, 4, 10823, 0), (256, 37, 10841, 0), (384, 20, 10443, 0),
     (132, 11, 10462, 0), (1024, 9, 11621, 0), (640, 40, 11631, 0), (2052, 7, 10822, 0), (4096, 70, 10434, 128),
     (128, 64, 32, 256),                                                     # step_vec4_kernel for every row
+    (256, 37, 200, 128), (1024, 700, 200, 0), (4096, 200, 204, 256), (12, 9, 200, 0),  # step_loop_kernel (cooperative)
+    (127, 33, 201, 0), (640, 300, 201, 0), (1, 5, 200, 0), (64, 64, 204, 0),
 ])
 def test_strict_steps_bit_exact_vs_oracle(gpu, pkg, orc, nx, ny, kernel, block):
     p, obst, cells0 = random_case(orc, nx, ny, seed=nx * 1000 + ny)
@@ -143,7 +145,7 @@ def test_av_vels_identical_across_kernel_variants(gpu, pkg, orc):
     same sums bit for bit."""
     p, obst, cells0 = random_case(orc, 256, 40, seed=7)
     ref = None
-    for kernel, block in [(0, 0), (10, 128), (21, 512), (99, 0), (99, 128), (10823, 0), (10444, 128), (11631, 0)]:
+    for kernel, block in [(0, 0), (10, 128), (21, 512), (99, 0), (99, 128), (10823, 0), (10444, 128), (11631, 0), (201, 0), (204, 0)]:
         with pkg.Lattice(to_param(p), obst, kernel=kernel, block=block) as lat:
             lat.upload(cells0)
             lat.run(9)
