@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <vector>
 
@@ -385,15 +386,39 @@ int make_tensor_maps(lbm_lattice* L, Slab& s)
     return LBM_OK;
 }
 
+// LBM_DEBUG=1: wall-clock phases of lattice creation on stderr
+struct DebugTimer {
+    bool on;
+    double t0;
+    static double now()
+    {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + ts.tv_nsec * 1e-9;
+    }
+    DebugTimer() : on(getenv("LBM_DEBUG") != nullptr), t0(now()) {}
+    void lap(const char* what)
+    {
+        if (!on) return;
+        const double t = now();
+        fprintf(stderr, "[lbm] %-28s %8.3f ms\n", what, (t - t0) * 1e3);
+        t0 = t;
+    }
+};
+
 int alloc_slab(lbm_lattice* L, Slab& s, const int* obst_rows_host)
 {
+    DebugTimer dbg;
     CU(cudaSetDevice(s.device));
     CU(cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking));
     s.stream = s.own_stream;
     CU(cudaEventCreate(&s.ev0));
     CU(cudaEventCreate(&s.ev1));
     const size_t pf = plane_floats(L, s);
-    for (int i = 0; i < 2; i++) CU(cudaMalloc(&s.lat[i], pf * Q * sizeof(float)));
+    dbg.lap("stream + events");
+    CU(cudaMalloc(&s.lat[0], 2 * pf * Q * sizeof(float))); // both lattices in one allocation
+    s.lat[1] = s.lat[0] + pf * Q;
+    dbg.lap("cudaMalloc lattices");
     CU(cudaMalloc(&s.obst, static_cast<size_t>(s.rows) * L->opitch * sizeof(uint32_t)));
     CU(cudaMemsetAsync(s.obst, 0, static_cast<size_t>(s.rows) * L->opitch * sizeof(uint32_t), s.stream));
     CU(cudaMalloc(&s.fluid_dev, sizeof(unsigned long long)));
@@ -405,31 +430,32 @@ int alloc_slab(lbm_lattice* L, Slab& s, const int* obst_rows_host)
     CU(cudaMalloc(&s.state_sums, (SUM_WORDS + 1) * sizeof(unsigned long long)));
     CU(cudaMalloc(&s.loop_barrier, 128));
 
-    // initial state: every cell, obstacles included (SerialCode:551-567); both lattices
-    const float w[Q] = {L->w0, L->w1, L->w1, L->w1, L->w1, L->w2, L->w2, L->w2, L->w2};
-    for (int i = 0; i < 2; i++)
-        for (int k = 0; k < Q; k++) {
-            fill_kernel<<<592, 256, 0, s.stream>>>(s.lat[i] + k * pf, pf, w[k]);
-            L->launches++;
-        }
-    CU(cudaGetLastError());
-
-    // obstacle map: stage the int rows, pack to bits on the device, count fluid cells
+    // obstacle map first: the int rows (4 B per cell) are staged in the memory of the second lattice
+    // (36 B per cell, not initialised yet) -- no temporary allocation, no cudaFree on the creation path --
+    // packed to bits on the device, and the fluid cells counted
     {
         const size_t n = static_cast<size_t>(s.rows) * L->p.nx;
-        int* staging = nullptr;
-        CU(cudaMalloc(&staging, n * sizeof(int)));
+        int* staging = reinterpret_cast<int*>(s.lat[1]);
+        dbg.lap("small allocs");
         CU(cudaMemcpyAsync(staging, obst_rows_host, n * sizeof(int), cudaMemcpyHostToDevice, s.stream));
         const size_t warps = static_cast<size_t>(s.rows) * ((L->p.nx + 31) / 32);
-        const size_t blocks = (warps * 32 + 255) / 256;
+        const size_t blocks = std::min<size_t>((warps * 32 + 255) / 256, 148 * 16);
         pack_obstacles_kernel<<<static_cast<unsigned>(blocks), 256, 0, s.stream>>>(staging, s.obst, L->p.nx, s.rows,
                                                                                     L->opitch, s.fluid_dev);
         L->launches++;
         CU(cudaGetLastError());
+        // initial state: every cell, obstacles included (SerialCode:551-567); both lattices
+        const float w[Q] = {L->w0, L->w1, L->w1, L->w1, L->w1, L->w2, L->w2, L->w2, L->w2};
+        for (int i = 0; i < 2; i++)
+            for (int k = 0; k < Q; k++) {
+                fill_kernel<<<592, 256, 0, s.stream>>>(s.lat[i] + k * pf, pf, w[k]);
+                L->launches++;
+            }
+        CU(cudaGetLastError());
         unsigned long long fl = 0;
         CU(cudaMemcpyAsync(&fl, s.fluid_dev, sizeof fl, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaStreamSynchronize(s.stream));
-        CU(cudaFree(staging));
+        dbg.lap("H2D + pack + fill (sync)");
         s.fluid = static_cast<long long>(fl);
     }
     return LBM_OK;
@@ -729,7 +755,7 @@ void free_slab(Slab& s)
     destroy_graphs(s);
     for (int i = 0; i < 2; i++)
         if (s.ipc_open[i]) cudaIpcCloseMemHandle(s.ipc_open[i]);
-    for (int i = 0; i < 2; i++) cudaFree(s.lat[i]);
+    cudaFree(s.lat[0]); // both lattices
     cudaFree(s.obst);
     cudaFree(s.fluid_dev);
     cudaFree(s.halo_block);
