@@ -269,7 +269,7 @@ def main() -> int:
     barrier()
     launches0 = lat.kernel_launches
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("BENCH_NO_CLOCKS"):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -279,7 +279,9 @@ def main() -> int:
     torch.cuda.synchronize()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get("LBM_DEBUG"):
+        lat.last_run_ms()
+    clocks = sampler.stop() if (rank == 0 and sampler.is_alive()) else None
     launches = lat.kernel_launches - launches0
     if dist is not None:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)

@@ -93,10 +93,12 @@ struct Slab {
     int* ctrl = nullptr;
     int* error = nullptr;
     unsigned long long* sums = nullptr;
+    unsigned long long** sums_ref = nullptr; // device word holding `sums` (what the graph kernels read)
     size_t sums_steps = 0;
     unsigned long long* state_sums = nullptr; // SUM_WORDS u64 + 1 double
     cudaGraphExec_t graph[2] = {nullptr, nullptr}; // by parity of the source lattice
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> dbg_events; // LBM_DEBUG: one per graph replay of the last run
     // launch geometry of step_vec4_kernel / step_scalar_kernel
     int tw_shift = 0, nbx = 0, ngroups = 0, nxv = 0, block = 0, nslots = 1;
     unsigned grid = 0;    // every row (mode 0)
@@ -527,7 +529,7 @@ StepArgs make_args(const lbm_lattice* L, const Slab& s, int src, int step_offset
     a.error = s.error;
     a.obst = s.obst;
     a.ctrl = s.ctrl;
-    a.sums = s.sums;
+    a.sums_ref = s.sums_ref;
     a.nslots = s.nslots;
     a.step_offset = step_offset;
     a.nx = L->p.nx, a.nxv = s.nxv, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
@@ -548,7 +550,7 @@ TmaArgs make_tma_args(const lbm_lattice* L, const Slab& s, int src, int step_off
     a.east[0] = in + 3 * pf, a.east[1] = in + 6 * pf, a.east[2] = in + 7 * pf;
     a.obst = s.obst;
     a.ctrl = s.ctrl;
-    a.sums = s.sums;
+    a.sums_ref = s.sums_ref;
     a.nslots = s.nslots;
     a.step_offset = step_offset;
     a.nx = L->p.nx, a.pitch = L->pitch, a.opitch = L->opitch;
@@ -644,21 +646,51 @@ int build_graph(lbm_lattice* L, Slab& s, int parity)
 
 int ensure_sums(lbm_lattice* L, Slab& s, size_t steps)
 {
+    (void)L;
     CU(cudaSetDevice(s.device));
+    if (!s.sums_ref) CU(cudaMalloc(&s.sums_ref, sizeof(unsigned long long*)));
     if (steps > s.sums_steps) {
-        if (s.sums) CU(cudaFree(s.sums));
+        if (s.sums) {
+            CU(cudaStreamSynchronize(s.stream));
+            CU(cudaFree(s.sums));
+        }
         s.sums = nullptr;
         size_t cap = s.sums_steps ? s.sums_steps : 1024;
         while (cap < steps) cap *= 2;
         CU(cudaMalloc(&s.sums, cap * s.nslots * SUM_WORDS * sizeof(unsigned long long)));
         s.sums_steps = cap;
-        destroy_graphs(s); // the graphs hold the old pointer
+        // the step graphs read the base through sums_ref: nothing to rebuild
+        CU(cudaMemcpyAsync(s.sums_ref, &s.sums, sizeof(unsigned long long*), cudaMemcpyHostToDevice, s.stream));
+        CU(cudaStreamSynchronize(s.stream)); // &s.sums must stay valid until the copy has happened
     }
     CU(cudaMemsetAsync(s.sums, 0, steps * s.nslots * SUM_WORDS * sizeof(unsigned long long), s.stream));
     return LBM_OK;
 }
 
 bool uses_halo(const lbm_lattice* L) { return L->per_process || L->nslabs > 1; }
+
+// Build, instantiate and upload the step graphs of both lattice parities when the lattice is created /
+// connected, not inside the first lbm_run that needs them: cudaGraphInstantiate was measured to take
+// anything from 1 ms to 100 ms on a busy host, and a run that starts with the device idle behind it
+// loses that much (profiles/r01_variance.md).
+int prepare_graphs(lbm_lattice* L)
+{
+    if (!L->opt.use_graph || L->interleaved) return LBM_OK;
+    for (int i = 0; i < L->nslabs; i++) {
+        Slab& s = L->slabs[i];
+        if (s.use_loop) continue;
+        int rc = ensure_sums(L, s, 1024);
+        if (rc) return rc;
+        for (int parity = 0; parity < 2; parity++) {
+            if (s.graph[parity]) continue;
+            rc = build_graph(L, s, parity);
+            if (rc) return rc;
+            CU(cudaGraphUpload(s.graph[parity], s.stream));
+        }
+        CU(cudaStreamSynchronize(s.stream));
+    }
+    return LBM_OK;
+}
 
 int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t* opt)
 {
@@ -762,6 +794,7 @@ void free_slab(Slab& s)
     cudaFree(s.ctrl);
     cudaFree(s.error);
     cudaFree(s.sums);
+    cudaFree(s.sums_ref);
     cudaFree(s.state_sums);
     cudaFree(s.loop_barrier);
     if (s.ev0) cudaEventDestroy(s.ev0);
@@ -978,6 +1011,14 @@ int lbm_create_on(const lbm_param_t* params, const int* obstacles, int nslabs, c
     } else {
         L->connected = true;
     }
+    rc = prepare_graphs(L);
+    if (rc) {
+        char keep[sizeof g_err];
+        memcpy(keep, g_err, sizeof keep);
+        lbm_destroy(L);
+        memcpy(g_err, keep, sizeof keep);
+        return rc;
+    }
     *out = L;
     return LBM_OK;
 }
@@ -1077,7 +1118,7 @@ int lbm_halo_connect(lbm_lattice_t* L, const void* south_handle, const void* nor
     s.peer_ring_s = ring_n_of(base[0]), s.peer_flag_s = flag_n_of(base[0]);
     s.peer_ring_n = ring_s_of(base[1]), s.peer_flag_n = flag_s_of(base[1]);
     L->connected = true;
-    return LBM_OK;
+    return prepare_graphs(L);
 }
 
 int lbm_set_stream(lbm_lattice_t* L, void* cuda_stream)
@@ -1168,6 +1209,12 @@ int lbm_run(lbm_lattice_t* L, int iters)
                 CU(cudaSetDevice(s.device));
                 CU(cudaGraphLaunch(s.graph[parity], s.stream));
                 L->launches += GRAPH_STEPS * (s.use_tma ? 2 : 1) + 1;
+                if (i == 0 && getenv("LBM_DEBUG") && s.dbg_events.size() < 256) {
+                    cudaEvent_t e;
+                    CU(cudaEventCreate(&e));
+                    CU(cudaEventRecord(e, s.stream));
+                    s.dbg_events.push_back(e);
+                }
             }
             done += GRAPH_STEPS;
         }
@@ -1442,6 +1489,20 @@ int lbm_last_run_ms(lbm_lattice_t* L, float* ms)
     }
     CU(cudaSetDevice(L->slabs[0].device));
     CU(cudaEventElapsedTime(ms, L->slabs[0].ev0, L->slabs[0].ev1));
+    if (!L->slabs[0].dbg_events.empty()) {
+        // LBM_DEBUG: device time of every graph replay (a gap = the host was late with the next launch)
+        fprintf(stderr, "[lbm] graph replays (ms):");
+        cudaEvent_t prev = L->slabs[0].ev0;
+        for (cudaEvent_t e : L->slabs[0].dbg_events) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, prev, e);
+            fprintf(stderr, " %.2f", t);
+            prev = e;
+        }
+        fprintf(stderr, "\n");
+        for (cudaEvent_t e : L->slabs[0].dbg_events) cudaEventDestroy(e);
+        L->slabs[0].dbg_events.clear();
+    }
     return LBM_OK;
 }
 

@@ -59,7 +59,7 @@ struct TmaArgs {
     const float* east[3];    // source planes 3,6,7 (periodic column 0 for x0+4 == nx)
     const uint32_t* obst;
     const int* ctrl;
-    unsigned long long* sums;
+    unsigned long long* const* sums_ref; // see StepArgs
     int nslots, step_offset;
     int nx, pitch, opitch;
     int y_first, y_end;      // rows [y_first, y_end) of the slab are this kernel's
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(32 * TY + 32, MINB)
     if (tid == 0) {
         const int s_abs = a.ctrl[0] + a.step_offset;
         unsigned long long* out =
-            a.sums + (static_cast<size_t>(s_abs - a.ctrl[1]) * a.nslots + (blockIdx.x & (a.nslots - 1))) * SUM_WORDS;
+            *a.sums_ref + (static_cast<size_t>(s_abs - a.ctrl[1]) * a.nslots + (blockIdx.x & (a.nslots - 1))) * SUM_WORDS;
         atomicAdd(&out[0], s_acc[0]);
         atomicAdd(&out[1], s_acc[1]);
         if (s_acc[2]) atomicAdd(&out[2], s_acc[2]);
