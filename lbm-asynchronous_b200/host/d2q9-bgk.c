@@ -20,11 +20,16 @@
  *   LBM_ARITH=strict|fast    collision arithmetic (default strict: bit-identical to SerialCode)
  *   LBM_SKIP_FINAL_STATE=1   do not write final_state.dat (87 bytes per cell of text)
  *   LBM_KERNEL, LBM_BLOCK    kernel variant / CTA size (tuning)
+ *   LBM_ANIMATION_EVERY=N    write animation_data/velocity_magnitude_%06d.dat after every N-th timestep
+ *                            (tt = 0, N, 2N, ...), the frames Visualization/animation.py reads.  Off by
+ *                            default: the reference ships with these calls commented out
+ *                            (SerialCode/d2q9-bgk.c:171-173, write_animation_data :802-849)
  */
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <sys/time.h>
 #include <unistd.h>
 
@@ -204,6 +209,20 @@ static void write_av_vels(const lbm_param_t* p, const float* av_vels)
     fclose(fp);
 }
 
+/* one animation frame: header, then |u| of every cell in row-major order, "%.6E" (SerialCode:802-849) */
+static void write_animation_frame(const lbm_param_t* p, const float* u, int timestep)
+{
+    char filename[256];
+    snprintf(filename, sizeof filename, "animation_data/velocity_magnitude_%06d.dat", timestep);
+    FILE* fp = fopen(filename, "w");
+    if (!fp) DIE("could not open animation data file");
+    fprintf(fp, "# nx=%d ny=%d timestep=%d\n", p->nx, p->ny, timestep);
+    const size_t n = (size_t)p->nx * (size_t)p->ny;
+    for (size_t c = 0; c < n; c++) fprintf(fp, "%.6E\n", u[c]);
+    fclose(fp);
+    printf("Written animation data for timestep %d\n", timestep);
+}
+
 static int env_int(const char* name, int dflt)
 {
     const char* v = getenv(name);
@@ -243,13 +262,40 @@ int main(int argc, char* argv[])
     const double init_toc = wall_seconds();
 
     /* ---- compute: the whole `for tt` loop runs on the device (SerialCode:166-169) ---- */
-    LBM_CALL(lbm_run(lat, params.maxIters));
-    LBM_CALL(lbm_sync(lat));
+    const int frame_every = env_int("LBM_ANIMATION_EVERY", 0);
+    float device_ms = 0.f;
+    if (frame_every <= 0) {
+        LBM_CALL(lbm_run(lat, params.maxIters));
+        LBM_CALL(lbm_sync(lat));
+        LBM_CALL(lbm_last_run_ms(lat, &device_ms));
+    } else {
+        /* frames after timestep tt = 0, N, 2N, ...: run up to the next frame, collect that chunk's av_vels */
+        mkdir("animation_data", 0777);
+        float* frame = malloc(sizeof(float) * (size_t)params.nx * (size_t)params.ny);
+        if (!frame) DIE("cannot allocate memory for the animation frame");
+        int done = 0;
+        while (done < params.maxIters) {
+            const int next_frame_tt = ((done + frame_every - 1) / frame_every) * frame_every; /* first tt >= done on the grid */
+            int chunk = next_frame_tt - done + 1;
+            if (chunk > params.maxIters - done) chunk = params.maxIters - done;
+            float ms = 0.f;
+            LBM_CALL(lbm_run(lat, chunk));
+            LBM_CALL(lbm_av_vels(lat, av_vels + done, chunk));
+            LBM_CALL(lbm_last_run_ms(lat, &ms));
+            device_ms += ms;
+            done += chunk;
+            if ((done - 1) % frame_every == 0) {
+                LBM_CALL(lbm_final_state(lat, NULL, NULL, frame, NULL));
+                write_animation_frame(&params, frame, done - 1);
+            }
+        }
+        free(frame);
+    }
     const double comp_toc = wall_seconds();
 
     /* ---- collate: per-step sums -> av_vels, moments of the final state -> host (the MPI variants'
      * gather + MPI_Reduce, MPI/d2q9-bgk.c:265-309) ---- */
-    LBM_CALL(lbm_av_vels(lat, av_vels, params.maxIters));
+    if (frame_every <= 0) LBM_CALL(lbm_av_vels(lat, av_vels, params.maxIters));
     const size_t n = (size_t)params.nx * (size_t)params.ny;
     float *ux = NULL, *uy = NULL, *u = NULL, *pressure = NULL;
     if (!skip_final) {
@@ -262,8 +308,6 @@ int main(int argc, char* argv[])
     }
     float av_final = 0.f;
     LBM_CALL(lbm_av_velocity(lat, &av_final));
-    float device_ms = 0.f;
-    LBM_CALL(lbm_last_run_ms(lat, &device_ms));
     const double col_toc = wall_seconds();
 
     /* ---- report (SerialCode:194-201); calc_reynolds :637-642 ---- */

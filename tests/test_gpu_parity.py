@@ -419,3 +419,31 @@ def test_host_program_end_to_end(gpu, built, orc, tmp_path):
     first = open(tmp_path / "final_state.dat").readline()
     assert first == "0 0 0.000000000000E+00 0.000000000000E+00 0.000000000000E+00 3.333333507180E-02 1\n"
     assert open(tmp_path / "av_vels.dat").readline().startswith("0:\t")
+
+
+def test_host_program_animation_frames(gpu, built, orc, tmp_path):
+    """LBM_ANIMATION_EVERY=N: the frames of write_animation_data() (SerialCode/d2q9-bgk.c:802-849), after
+    timesteps tt = 0, N, 2N, ...; chunked runs leave av_vels.dat and final_state.dat unchanged."""
+    exe = os.path.join(ROOT, "lbm-asynchronous_b200", "d2q9-bgk")
+    grid, iters, every = "128x128", 120, 50
+    tok = open(os.path.join(INPUTS, f"input_{grid}.params")).read().split()
+    pf = tmp_path / "p.params"
+    pf.write_text("\n".join(tok[:2] + [str(iters)] + tok[3:]) + "\n")
+    of = os.path.join(INPUTS, f"obstacles_{grid}.dat")
+    outs = {}
+    for name, env in (("plain", {}), ("frames", {"LBM_ANIMATION_EVERY": str(every)})):
+        wd = tmp_path / name
+        wd.mkdir()
+        r = subprocess.run([exe, str(pf), of], cwd=wd, capture_output=True, text=True, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr
+        outs[name] = (open(wd / "av_vels.dat").read(), open(wd / "final_state.dat").read(), r.stdout)
+    assert outs["plain"][0] == outs["frames"][0] and outs["plain"][1] == outs["frames"][1]
+    p, obst = load_case(orc, grid)
+    for tt in (0, 50, 100):
+        assert f"Written animation data for timestep {tt}\n" in outs["frames"][2]
+        lines = open(tmp_path / "frames" / "animation_data" / f"velocity_magnitude_{tt:06d}.dat").read().splitlines()
+        assert lines[0] == f"# nx={p.nx} ny={p.ny} timestep={tt}"
+        cells, _ = orc.run(p, obst, tt + 1)
+        _, _, u, _ = orc.final_state(p, cells, obst)
+        assert lines[1:] == ["%.6E" % v for v in u.ravel()]
+    assert not os.path.exists(tmp_path / "frames" / "animation_data" / "velocity_magnitude_000119.dat")
