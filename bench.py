@@ -387,6 +387,12 @@ def main() -> int:
                 except Exception as ex:
                     others[prog] = f"failed: {str(ex)[:80]}"
             line["cpu_baseline"]["mpi_programs_mlups"] = others
+            try:  # SerialCode on one core, a smaller sample (it is ~15x slower)
+                sv, _, sk = run_reference_cpu(nx, 256, 5, 1, program="serial")
+                if sk == "reference":
+                    line["cpu_baseline"]["serial_1core_mlups"] = round(sv, 1)
+            except Exception as ex:
+                line["cpu_baseline"]["serial_1core_mlups"] = f"failed: {str(ex)[:80]}"
         except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
             line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": cores, "kind": "reference", "sample": f"failed: {ex}"}
     print(json.dumps(line), flush=True)
