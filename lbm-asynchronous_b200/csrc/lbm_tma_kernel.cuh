@@ -216,25 +216,16 @@ __global__ void __launch_bounds__(32 * TY + 32, MINB)
             if (east) sh[3] = e3, sh[6] = e6, sh[7] = e7;
 
             const uint32_t obits = (oword >> (x0 & 31)) & 0xfu;
-            const bool accel = accel_live && (y == a.accel_row);
+            float t[Q][4];
+#pragma unroll
+            for (int k = 0; k < Q; k++) {
+                const float e[6] = {sh[k], v[k].x, v[k].y, v[k].z, v[k].w, sh[k]};
+#pragma unroll
+                for (int j = 0; j < 4; j++) t[k][j] = e[j + 1 - dir_cx(k)]; // cell x0+j pulls column x0+j-cx
+            }
             float o[Q][4];
             SpeedAcc acc = {0u, 0u, 0u}; // this tile's four cells: lo < 2^26, hi < 2^20
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                float t[Q];
-#pragma unroll
-                for (int k = 0; k < Q; k++) {
-                    const float e[6] = {sh[k], v[k].x, v[k].y, v[k].z, v[k].w, sh[k]};
-                    t[k] = e[j + 1 - dir_cx(k)]; // cell x0+j pulls column x0+j-cx
-                }
-                const bool solid = (obits >> j) & 1u;
-                float oc[Q];
-                const float sp = update_cell<STRICT>(t, solid, a.omega, oc);
-                acc_speed(acc, sp, valid && !solid);
-                if (accel) accelerate_cell(oc, solid, a.w1a, a.w2a);
-#pragma unroll
-                for (int k = 0; k < Q; k++) o[k][j] = oc[k];
-            }
+            update4<STRICT>(t, obits, valid, accel_live && (y == a.accel_row), a.omega, a.w1a, a.w2a, o, acc);
             acc_lo += acc.lo, acc_hi += acc.hi, acc_bad += acc.bad;
 
             if (valid) {
