@@ -1400,15 +1400,12 @@ int lbm_final_state(lbm_lattice_t* L, float* u_x, float* u_y, float* u, float* p
         Slab& s = L->slabs[i];
         CU(cudaSetDevice(s.device));
         const size_t n = static_cast<size_t>(L->p.nx) * s.rows;
+        // scratch: the lattice that does NOT hold the current state (9 planes of rows*pitch >= 4 planes of
+        // rows*nx floats); the next lbm_run overwrites it anyway.  No allocation on this path.
+        float* scratch = s.lat[L->cur ^ 1];
         float* dev[4] = {nullptr, nullptr, nullptr, nullptr};
         for (int q = 0; q < 4; q++)
-            if (host[q]) {
-                cudaError_t e = cudaMalloc(&dev[q], n * sizeof(float));
-                if (e != cudaSuccess) {
-                    for (int z = 0; z < q; z++) cudaFree(dev[z]);
-                    return fail(LBM_ENOMEM, "cudaMalloc of a final-state plane failed: %s", cudaGetErrorString(e));
-                }
-            }
+            if (host[q]) dev[q] = scratch + static_cast<size_t>(q) * n;
         rc = run_state_kernel(L, s, dev, false, false);
         const size_t off = static_cast<size_t>(s.row0 - base_row) * L->p.nx;
         for (int q = 0; q < 4 && !rc; q++)
@@ -1416,8 +1413,8 @@ int lbm_final_state(lbm_lattice_t* L, float* u_x, float* u_y, float* u, float* p
                 cudaError_t e = cudaMemcpyAsync(host[q] + off, dev[q], n * sizeof(float), cudaMemcpyDeviceToHost, s.stream);
                 if (e != cudaSuccess) rc = fail(LBM_ECUDA, "final-state download failed: %s", cudaGetErrorString(e));
             }
-        cudaStreamSynchronize(s.stream);
-        for (int q = 0; q < 4; q++) cudaFree(dev[q]);
+        cudaError_t es = cudaStreamSynchronize(s.stream);
+        if (!rc && es != cudaSuccess) rc = fail(LBM_ECUDA, "final-state download failed: %s", cudaGetErrorString(es));
         if (rc) return rc;
     }
     return LBM_OK;
@@ -1432,8 +1429,8 @@ static int layout_copy(lbm_lattice_t* L, lbm_speed_t* cells, bool download)
         Slab& s = L->slabs[i];
         CU(cudaSetDevice(s.device));
         const size_t n = static_cast<size_t>(L->p.nx) * s.rows;
-        float* aos = nullptr;
-        CU(cudaMalloc(&aos, n * Q * sizeof(float)));
+        // AoS staging in the lattice that does not hold the current state (9*rows*pitch >= 9*rows*nx floats)
+        float* aos = s.lat[L->cur ^ 1];
         LayoutArgs a;
         const size_t pf = plane_floats(L, s);
         for (int k = 0; k < Q; k++) a.f[k] = s.lat[L->cur] + k * pf;
@@ -1450,7 +1447,6 @@ static int layout_copy(lbm_lattice_t* L, lbm_speed_t* cells, bool download)
         }
         L->launches++;
         cudaError_t e2 = cudaStreamSynchronize(s.stream);
-        cudaFree(aos);
         if (e != cudaSuccess || e2 != cudaSuccess)
             return fail(LBM_ECUDA, "cell %s failed: %s", download ? "download" : "upload",
                         cudaGetErrorString(e != cudaSuccess ? e : e2));
