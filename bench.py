@@ -41,7 +41,6 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
 BYTES_PER_LUP = 72.0  # 9 fp32 read + 9 fp32 written per lattice update
-L2_BYTES = 126e6
 
 
 def measured_peak():

@@ -1,3 +1,5 @@
+"""Debug helper: run a few steps of one small random case through the C ABI with a chosen kernel code and
+report where the lattice differs from the oracle.  usage: python tools/debug_small_case.py [kernel [nx ny]]"""
 import sys, numpy as np
 sys.path.insert(0, "/root/repo")
 import __graft_entry__ as e
