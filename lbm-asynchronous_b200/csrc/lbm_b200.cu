@@ -108,7 +108,7 @@ struct Slab {
     // whole runs in one cooperative launch (step_loop_kernel), L2-resident single-slab grids
     bool use_loop = false;
     unsigned loop_grid = 0;
-    int loop_vec = 4, loop_block = 256, loop_tw_shift = 0, loop_nbx = 0, loop_nxv = 0, loop_ntiles = 0;
+    int loop_vec = 4, loop_block = 256, loop_tw_shift = 0, loop_nbx = 0, loop_nby = 0, loop_nxv = 0, loop_ntiles = 0;
     unsigned* loop_barrier = nullptr;
     // interior rows through step_tma_kernel
     bool use_tma = false;
@@ -213,9 +213,10 @@ bool tma_by_shape(int ty, int stages, int minb, TmaChoice* c)
 //   99           step_scalar_kernel for every row
 //   200          step_loop_kernel (all steps of a run in one cooperative launch); also the default for
 //                single-slab grids whose two lattices fit in L2 (<= LOOP_MAX_CELLS cells).  201 / 204 force
-//                its 1-cell / 4-cell per thread mapping (default: 1 cell below LOOP_VEC4_CELLS cells)
+//                its 1-cell / 4-cell per thread mapping (default: 1 cell up to LOOP_VEC4_CELLS cells per slab)
 constexpr long long LOOP_MAX_CELLS = 1400000; // 2 x 36 B x cells <= ~100 MB of the 126 MB L2
-constexpr long long LOOP_VEC4_CELLS = 300000; // below this a grid cannot fill the SMs with 4 cells per thread
+constexpr long long LOOP_VEC4_CELLS = 70000;  // up to 256 x 256: one cell per thread (<= 512 CTAs of 128 threads) beats four;
+                                              // above, the one-counter grid barrier gets too slow for that many CTAs
 struct KernelChoice {
     bool loop;
     bool vec4;
@@ -305,12 +306,17 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
     s.ngroups = (s.rows + th - 1) / th;
     s.grid = static_cast<unsigned>(s.nbx) * static_cast<unsigned>(s.ngroups);
     s.grid_b = static_cast<unsigned>(s.nbx) * (s.rows >= 2 ? 2u : 1u);
-    // step loop: single slab without halos; tiles strided over the CTAs that are resident at once
+    // step loop: tiles strided over the CTAs that are resident at once.  With several slabs every slab must have
+    // a GPU of its own (the resident kernels exchange flags), and every rank must take the same decisions, so they
+    // are based on the nominal slab height ceil(ny / slabs), not on this slab's own row count
     s.use_loop = false;
-    if (k.loop && L->opt.use_graph && !uses_halo_cfg(L) &&
-        (L->opt.kernel >= 200 || static_cast<long long>(L->p.nx) * s.rows <= LOOP_MAX_CELLS)) {
-        const long long cells = static_cast<long long>(L->p.nx) * s.rows;
-        bool v4 = k.vec4 && cells >= LOOP_VEC4_CELLS;
+    const int total_slabs = L->per_process ? L->nranks : L->nslabs;
+    const long long nominal_cells = static_cast<long long>(L->p.nx) * ((L->p.ny + total_slabs - 1) / total_slabs);
+    // default: single slab only -- across GPUs the resident kernels measured no better than the graph path
+    // (profiles/r01_small_grids.md); kernel codes 200/201/204 ask for it explicitly
+    if (k.loop && L->opt.use_graph && !L->interleaved &&
+        (L->opt.kernel >= 200 || (total_slabs == 1 && nominal_cells <= LOOP_MAX_CELLS))) {
+        bool v4 = k.vec4 && nominal_cells >= LOOP_VEC4_CELLS;
         if (L->opt.kernel == 201) v4 = false;
         if (L->opt.kernel == 204) v4 = k.vec4;
         s.loop_vec = v4 ? 4 : 1;
@@ -327,6 +333,7 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
         if (g > ntiles) g = ntiles;
         if (g >= 1 && ntiles <= 0x7fffffffLL && L->loop_kernel[v4 ? 1 : 0]) {
             s.loop_ntiles = static_cast<int>(ntiles);
+            s.loop_nby = (s.rows + lth - 1) / lth;
             s.loop_grid = static_cast<unsigned>(g);
             s.use_loop = true;
         }
@@ -499,34 +506,34 @@ void destroy_graphs(Slab& s)
         }
 }
 
+HaloCfg make_halo_cfg(const lbm_lattice* L, const Slab& s)
+{
+    HaloCfg h;
+    memset(&h, 0, sizeof h);
+    h.on = (L->per_process || L->nslabs > 1) ? 1 : 0;
+    if (h.on) {
+        h.hs.recv_ring = s.ring_s, h.hs.send_ring = s.peer_ring_s, h.hs.wait = s.flag_s, h.hs.signal = s.peer_flag_s;
+        h.hn.recv_ring = s.ring_n, h.hn.send_ring = s.peer_ring_n, h.hn.wait = s.flag_n, h.hn.signal = s.peer_flag_n;
+    }
+    h.wait = (L->opt.halo_mode == LBM_HALO_SYNC) ? 1 : 0;
+    h.ring = L->ring;
+    h.lag = (L->opt.halo_mode == LBM_HALO_SYNC) ? L->opt.halo_lag : 0;
+    h.ctas_per_row = static_cast<unsigned>(s.use_loop ? s.loop_nbx : s.nbx);
+    h.slot_stride = 3ull * L->pitch;
+    h.timeout_ns = L->timeout_ns;
+    h.error = s.error;
+    return h;
+}
+
 StepArgs make_args(const lbm_lattice* L, const Slab& s, int src, int step_offset)
 {
     StepArgs a;
     memset(&a, 0, sizeof a);
     a.mode = s.use_tma ? 1 : 0;
-    const size_t pf = plane_floats(L, s);
-    for (int k = 0; k < Q; k++) {
-        a.in[k] = s.lat[src] + k * pf;
-        a.out[k] = s.lat[src ^ 1] + k * pf;
-    }
-    const bool halo = (L->per_process ? true : L->nslabs > 1);
-    a.halo = halo ? 1 : 0;
-    if (!halo) {
-        // periodic wrap in y inside the lattice (SerialCode:257-258): row 0 pulls from row ny-1, row ny-1 from row 0
-        const size_t last = static_cast<size_t>(s.rows - 1) * L->pitch;
-        a.wrap_s[0] = a.in[2] + last, a.wrap_s[1] = a.in[5] + last, a.wrap_s[2] = a.in[6] + last;
-        a.wrap_n[0] = a.in[4], a.wrap_n[1] = a.in[7], a.wrap_n[2] = a.in[8];
-    } else {
-        a.hs.recv_ring = s.ring_s, a.hs.send_ring = s.peer_ring_s, a.hs.wait = s.flag_s, a.hs.signal = s.peer_flag_s;
-        a.hn.recv_ring = s.ring_n, a.hn.send_ring = s.peer_ring_n, a.hn.wait = s.flag_n, a.hn.signal = s.peer_flag_n;
-    }
-    a.halo_wait = (L->opt.halo_mode == LBM_HALO_SYNC) ? 1 : 0;
-    a.ring = L->ring;
-    a.lag = (L->opt.halo_mode == LBM_HALO_SYNC) ? L->opt.halo_lag : 0;
-    a.ctas_per_row = static_cast<unsigned>(s.nbx);
-    a.slot_stride = 3ull * L->pitch;
-    a.timeout_ns = L->timeout_ns;
-    a.error = s.error;
+    a.pf = plane_floats(L, s);
+    a.in = s.lat[src];
+    a.out = s.lat[src ^ 1];
+    a.h = make_halo_cfg(L, s);
     a.obst = s.obst;
     a.ctrl = s.ctrl;
     a.sums_ref = s.sums_ref;
@@ -737,9 +744,14 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
         L->kernel = strict ? vec4_by_hint<true>(k.hint, k.block, k.minb) : vec4_by_hint<false>(k.hint, k.block, k.minb);
     else
         L->kernel = scalar_kernel(strict, k.block);
-    if (k.loop && !uses_halo_cfg(L)) {
-        L->loop_kernel[0] = strict ? step_loop_kernel<true, 128, 1> : step_loop_kernel<false, 128, 1>;
-        L->loop_kernel[1] = strict ? step_loop_kernel<true, 256, 4> : step_loop_kernel<false, 256, 4>;
+    if (k.loop && !L->interleaved) {
+        if (uses_halo_cfg(L)) {
+            L->loop_kernel[0] = strict ? step_loop_kernel<true, 128, 1, true> : step_loop_kernel<false, 128, 1, true>;
+            L->loop_kernel[1] = strict ? step_loop_kernel<true, 256, 4, true> : step_loop_kernel<false, 256, 4, true>;
+        } else {
+            L->loop_kernel[0] = strict ? step_loop_kernel<true, 128, 1, false> : step_loop_kernel<false, 128, 1, false>;
+            L->loop_kernel[1] = strict ? step_loop_kernel<true, 256, 4, false> : step_loop_kernel<false, 256, 4, false>;
+        }
         CU(cudaSetDevice(L->slabs[0].device));
         int sms = 0, coop = 0;
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, L->slabs[0].device));
@@ -838,7 +850,7 @@ int push_boundary_rows(lbm_lattice* L, Slab& s)
                                                   s.peer_ring_n, nx, L->pitch, L->ring, 3ull * L->pitch);
     L->launches += 2;
     CU(cudaGetLastError());
-    const unsigned long long v = static_cast<unsigned long long>(L->steps_done) * static_cast<unsigned>(s.nbx);
+    const unsigned long long v = static_cast<unsigned long long>(L->steps_done) * static_cast<unsigned>(s.use_loop ? s.loop_nbx : s.nbx);
     CU(cudaMemcpyAsync(s.peer_flag_s, &v, sizeof v, cudaMemcpyHostToDevice, s.stream));
     CU(cudaMemcpyAsync(s.peer_flag_n, &v, sizeof v, cudaMemcpyHostToDevice, s.stream));
     CU(cudaStreamSynchronize(s.stream));
@@ -928,6 +940,9 @@ static int create_common(const lbm_param_t* params, const lbm_options_t* opt, in
         const int g = params->ny - 2; // the driven row, SerialCode:226
         s.accel_row = (g >= s.row0 && g < s.row1) ? g - s.row0 : -1;
     }
+    for (int i = 0; i < nslabs; i++)
+        for (int j = 0; j < i; j++)
+            if (devices[j] == devices[i]) L->interleaved = true; // slabs sharing a device: step-major launches on one stream
     rc = common_setup(L, params, opt);
     for (int i = 0; i < nslabs && !rc; i++) {
         Slab& s = L->slabs[i];
@@ -1168,33 +1183,44 @@ int lbm_run(lbm_lattice_t* L, int iters)
     }
     int done = 0;
     const int parity = L->cur;
-    if (L->nslabs == 1 && L->slabs[0].use_loop) {
-        // every step of this run in cooperative launches of step_loop_kernel (one, unless the barrier
-        // counter of 32 bits would overflow)
-        Slab& s = L->slabs[0];
-        CU(cudaSetDevice(s.device));
-        const long long max_steps = 0xffffffffLL / s.loop_grid - 1;
+    bool all_loop = true;
+    for (int i = 0; i < L->nslabs; i++) all_loop = all_loop && L->slabs[i].use_loop;
+    if (all_loop) {
+        // every step of this run in cooperative launches of step_loop_kernel, one per slab (slabs on different
+        // GPUs run at the same time and exchange halo rows and flags); more than one launch per slab only if
+        // the 32-bit barrier counter would overflow
+        long long max_steps = iters;
+        for (int i = 0; i < L->nslabs; i++) max_steps = std::min<long long>(max_steps, 0xffffffffLL / L->slabs[i].loop_grid - 1);
         while (done < iters) {
             const int n = static_cast<int>(std::min<long long>(iters - done, max_steps));
-            LoopArgs a;
-            memset(&a, 0, sizeof a);
-            a.lat[0] = s.lat[0], a.lat[1] = s.lat[1];
-            a.pf = plane_floats(L, s);
-            a.obst = s.obst;
-            a.sums = s.sums + static_cast<size_t>(done) * s.nslots * SUM_WORDS;
-            a.barrier = s.loop_barrier;
-            a.nslots = s.nslots;
-            a.first_step = first + done, a.nsteps = n, a.last_step = first + iters - 1;
-            a.src = (parity + done) & 1;
-            a.nx = L->p.nx, a.nxv = s.loop_nxv, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
-            a.tw_shift = s.loop_tw_shift, a.nbx = s.loop_nbx, a.ntiles = s.loop_ntiles;
-            a.accel_row = s.accel_row;
-            a.omega = L->p.omega, a.w1a = L->w1a, a.w2a = L->w2a;
-            CU(cudaMemsetAsync(s.loop_barrier, 0, sizeof(unsigned), s.stream));
-            void* kp[1] = {&a};
-            CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(L->loop_kernel[s.loop_vec == 4 ? 1 : 0]), dim3(s.loop_grid),
-                                           dim3(s.loop_block), kp, 0, s.stream));
-            L->launches++;
+            for (int i = 0; i < L->nslabs; i++) {
+                Slab& s = L->slabs[i];
+                CU(cudaSetDevice(s.device));
+                LoopArgs a;
+                memset(&a, 0, sizeof a);
+                a.lat[0] = s.lat[0], a.lat[1] = s.lat[1];
+                a.pf = plane_floats(L, s);
+                a.h = make_halo_cfg(L, s);
+                a.obst = s.obst;
+                a.sums = s.sums + static_cast<size_t>(done) * s.nslots * SUM_WORDS;
+                a.barrier = s.loop_barrier;
+                a.nslots = s.nslots;
+                a.first_step = first + done, a.nsteps = n, a.last_step = first + iters - 1;
+                a.src = (parity + done) & 1;
+                a.nx = L->p.nx, a.nxv = s.loop_nxv, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
+                a.tw_shift = s.loop_tw_shift, a.nbx = s.loop_nbx, a.nby = s.loop_nby, a.ntiles = s.loop_ntiles;
+                {
+                    const int nb = (s.loop_nby >= 2 ? 2 : 1) * s.loop_nbx;
+                    a.nboundary = (a.h.on && static_cast<long long>(s.loop_grid) > nb && s.loop_ntiles > nb) ? nb : 0;
+                }
+                a.accel_row = s.accel_row;
+                a.omega = L->p.omega, a.w1a = L->w1a, a.w2a = L->w2a;
+                CU(cudaMemsetAsync(s.loop_barrier, 0, sizeof(unsigned), s.stream));
+                void* kp[1] = {&a};
+                CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(L->loop_kernel[s.loop_vec == 4 ? 1 : 0]),
+                                               dim3(s.loop_grid), dim3(s.loop_block), kp, 0, s.stream));
+                L->launches++;
+            }
             done += n;
         }
     }

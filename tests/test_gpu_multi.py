@@ -53,6 +53,24 @@ def test_sync_slabs_on_n_gpus_equal_one_gpu(ngpu, pkg, orc, grid, iters):
         assert np.array_equal(one[1], many[1]), n
 
 
+def test_resident_step_loop_across_gpus(ngpu, pkg, orc):
+    """kernel=200: step_loop_kernel on every GPU at once, halo rows and flags exchanged between the resident
+    kernels (not the default across GPUs: it measured no faster than the graph path).  Same bits."""
+    p, obst = load_case(orc, "1024x1024")
+    iters = 600
+    with pkg.Lattice(to_param(p), obst, ngpus=1) as lat:
+        lat.run(iters)
+        one = (lat.cells(), lat.tot_u_sums()[0])
+    for n, kernel in ((2, 200), (min(4, ngpu), 204), (2, 201)):
+        with pkg.Lattice(to_param(p), obst, ngpus=n, kernel=kernel) as lat:
+            lat.run(250)
+            lat.run(350)
+            many = (lat.cells(), lat.tot_u_sums()[0])
+            launches = lat.kernel_launches
+        assert np.array_equal(bits(one[0]), bits(many[0])), (n, kernel)
+        assert launches < 200  # a handful of cooperative launches, not one per step
+
+
 def test_async_halo_mode_drift_is_small(ngpu, pkg, orc):
     """The stale-halo mode (un-waited MPI_Testall): free running, so no bit-exact expectation and no
     reference fixture (parity unpinned).  Its drift against the synchronous run is
