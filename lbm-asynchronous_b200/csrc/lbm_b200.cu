@@ -598,8 +598,7 @@ int build_graph(lbm_lattice* L, Slab& s, int parity)
         {
             StepArgs a = make_args(L, s, src, j);
             void* kp[1] = {&a};
-            cudaKernelNodeParams np;
-            memset(&np, 0, sizeof np);
+            cudaKernelNodeParams np = {};
             np.func = reinterpret_cast<void*>(L->kernel);
             np.gridDim = dim3(s.use_tma ? s.grid_b : s.grid, 1, 1);
             np.blockDim = dim3(s.block, 1, 1);
@@ -619,8 +618,7 @@ int build_graph(lbm_lattice* L, Slab& s, int parity)
         if (s.use_tma) {
             TmaArgs t = make_tma_args(L, s, src, j);
             void* kp[3] = {&s.tmap[src], &s.tmapw[src], &t};
-            cudaKernelNodeParams np;
-            memset(&np, 0, sizeof np);
+            cudaKernelNodeParams np = {};
             np.func = reinterpret_cast<void*>(L->tma_kernel);
             np.gridDim = dim3(s.tma_grid, 1, 1);
             np.blockDim = dim3(32 * L->tma_ty + 32, 1, 1);
@@ -636,8 +634,7 @@ int build_graph(lbm_lattice* L, Slab& s, int parity)
         int* ctrl = s.ctrl;
         int by = GRAPH_STEPS;
         void* kp[2] = {&ctrl, &by};
-        cudaKernelNodeParams np;
-        memset(&np, 0, sizeof np);
+        cudaKernelNodeParams np = {};
         np.func = reinterpret_cast<void*>(advance_ctrl_kernel);
         np.gridDim = dim3(1, 1, 1);
         np.blockDim = dim3(32, 1, 1);
