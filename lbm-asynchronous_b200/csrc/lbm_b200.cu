@@ -233,7 +233,13 @@ KernelChoice choose_kernel(const lbm_options_t& o, int nx)
     k.minb = 1;
     k.block = (o.block == 128 || o.block == 256 || o.block == 512) ? o.block : 256;
     k.tma = k.vec4 && nx >= TMA_TX && (o.kernel == 0 || (o.kernel >= 200 && o.kernel <= 204) || o.kernel >= 10000);
-    k.tma_ty = 16, k.tma_stages = 2, k.tma_minb = 1; // best of the r01 sweep on 8192^2 and 32768x4096 (profiles/)
+    // best of the r01 sweeps (profiles/r01_variant_sweep.md): the strict flavour is instruction heavy and wants
+    // many consumer warps (16 rows x 2 stages), the fast flavour is load-latency bound and wants a deeper pipeline
+    // of smaller tiles (8 rows x 4 stages)
+    if (o.arith == LBM_ARITH_FAST)
+        k.tma_ty = 8, k.tma_stages = 4, k.tma_minb = 1;
+    else
+        k.tma_ty = 16, k.tma_stages = 2, k.tma_minb = 1;
     if (o.kernel >= 10000) {
         k.tma_ty = (o.kernel - 10000) / 100;
         k.tma_stages = (o.kernel / 10) % 10;
