@@ -292,6 +292,13 @@ def test_synthetic_channel_medium_bit_exact_vs_oracle(gpu, pkg, orc):
         cells, av = lat.cells(), lat.av_vels()
     assert_lattice_equal(cells, ref_cells, obst)
     np.testing.assert_allclose(av, ref_av, rtol=1e-4)
+    # the fast flavour on the same case (its own default tile shape): fp32 re-association only
+    with pkg.Lattice(to_param(p), obst, arith="fast") as lat:
+        lat.run(iters)
+        fcells, fav = lat.cells(), lat.av_vels()
+    fluid = obst == 0
+    np.testing.assert_allclose(fcells[fluid], ref_cells[fluid], rtol=2e-5, atol=1e-9)
+    np.testing.assert_allclose(fav, ref_av, rtol=1e-3)
 
 
 def test_full_size_8192_bit_exact_vs_oracle_and_slab_invariance(gpu, pkg, orc):
