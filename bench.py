@@ -205,6 +205,8 @@ def main() -> int:
     ap.add_argument("--halo-mode", default="sync", choices=["sync", "async"])
     ap.add_argument("--kernel", type=int, default=int(os.environ.get("LBM_KERNEL", "0")))
     ap.add_argument("--block", type=int, default=int(os.environ.get("LBM_BLOCK", "0")))
+    ap.add_argument("--developed", action="store_true",
+                    help="N=1 only: start from a perturbed state (every cell moving) instead of the uniform state at rest")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -258,6 +260,15 @@ def main() -> int:
         obst = pkg.channel_obstacles(nx, ny)
         lat = pkg.Lattice(param, obst, ngpus=1, **opts)
         runner = lat
+        if args.developed:
+            # every cell gets a small random velocity: no cell takes the "fluid at rest" shortcuts of the kernel
+            rng = np.random.default_rng(7)
+            cells0 = np.empty((ny, nx, 9), dtype=np.float32)
+            w = np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4, dtype=np.float32) * np.float32(0.1)
+            for k in range(9):
+                cells0[:, :, k] = w[k] * (1 + 0.02 * rng.standard_normal((ny, nx), dtype=np.float32))
+            lat.upload(cells0)
+            del cells0
     else:
         sh = ShardedLattice(param, lambda r0, r1: pkg.channel_obstacles(nx, ny, row0=r0, row1=r1), local_rank, **opts)
         lat = sh.slab
@@ -360,7 +371,7 @@ def main() -> int:
         "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": n, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(workload_config(n, nx, ny), arith=args.arith, halo_mode=args.halo_mode if n > 1 else None,
-                       kernel=args.kernel, block=args.block),
+                       kernel=args.kernel, block=args.block, initial_state="perturbed" if args.developed else "uniform at rest"),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_LUP * cells / n, "kernel": "lbm::step_tma_kernel",
