@@ -156,3 +156,15 @@ def test_gen_channel_matches_the_numpy_generator(built, pkg, orc, tmp_path):
     assert 0.02 < want[1:ny - 2].mean() < 0.08
     # a slab of rows is the same as slicing the full map
     assert np.array_equal(pkg.channel_obstacles(nx, ny, p=0.05, seed=42, row0=13, row1=31), want[13:31])
+
+
+def test_missing_library_fails_loudly(pkg, monkeypatch):
+    """No silent fallback: if liblbm_b200.so is not there, the Python layer raises instead of computing
+    anything some other way."""
+    from lbm_asynchronous_b200 import capi
+
+    monkeypatch.setattr(capi, "_lib", None)
+    monkeypatch.setattr(capi, "_LIB", "/nonexistent/liblbm_b200.so")
+    with pytest.raises(capi.LbmError) as e:
+        capi.library()
+    assert "is missing" in str(e.value) and "no CPU or PyTorch fallback" in str(e.value)
