@@ -390,11 +390,17 @@ int make_tensor_maps(lbm_lattice* L, Slab& s)
         const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(L->p.nx), static_cast<cuuint64_t>(s.rows), Q};
         const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(L->pitch) * sizeof(float), static_cast<cuuint64_t>(pf) * sizeof(float)};
         const cuuint32_t estride[3] = {1, 1, 1};
+        CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+        if (const char* e = getenv("LBM_TMA_L2PROMO")) { // tuning: 0 none, 64, 128, 256 (default)
+            const int v = atoi(e);
+            promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                           : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : promo));
+        }
         for (int w = 0; w < 2; w++) {
             const cuuint32_t box[3] = {static_cast<cuuint32_t>(w ? TMA_TXW : TMA_TX), static_cast<cuuint32_t>(L->tma_ty), 1};
             const CUresult r = encode(w ? &s.tmapw[i] : &s.tmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s.lat[i], gdim, gstride, box,
                                       estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                      promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(LBM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
         }
     }
