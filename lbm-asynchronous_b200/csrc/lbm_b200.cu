@@ -671,7 +671,7 @@ int ensure_sums(lbm_lattice* L, Slab& s, size_t steps)
             CU(cudaFree(s.sums));
         }
         s.sums = nullptr;
-        size_t cap = s.sums_steps ? s.sums_steps : 1024;
+        size_t cap = s.sums_steps ? s.sums_steps : 8192;
         while (cap < steps) cap *= 2;
         CU(cudaMalloc(&s.sums, cap * s.nslots * SUM_WORDS * sizeof(unsigned long long)));
         s.sums_steps = cap;
@@ -695,7 +695,7 @@ int prepare_graphs(lbm_lattice* L)
     for (int i = 0; i < L->nslabs; i++) {
         Slab& s = L->slabs[i];
         if (s.use_loop) continue;
-        int rc = ensure_sums(L, s, 1024);
+        int rc = ensure_sums(L, s, 8192);
         if (rc) return rc;
         for (int parity = 0; parity < 2; parity++) {
             if (s.graph[parity]) continue;
