@@ -182,7 +182,7 @@ int MPI_Init(int* argc, char*** argv)
     uint64_t off = round_up(sizeof(shared_hdr), 4096);
     for (int s = 0; s < g_size; s++)
         for (int d = 0; d < g_size; d++) {
-            if (s == d) continue;
+            if (s == d && g_size > 1) continue; /* a ring of one talks to itself */
             const int neighbour = (d == (s + 1) % g_size) || (d == (s - 1 + g_size) % g_size);
             const int root = (s == 0 || d == 0);
             if (!neighbour && !root) continue;
@@ -218,6 +218,7 @@ int MPI_Init(int* argc, char*** argv)
 int MPI_Barrier(MPI_Comm comm)
 {
     (void)comm;
+    progress(); /* every MPI call makes progress, also for the rank that arrives last and never spins */
     g_local_sense = !g_local_sense;
     if (__atomic_add_fetch(&g_hdr->barrier_count, 1, __ATOMIC_ACQ_REL) == g_size) {
         g_hdr->barrier_count = 0;
@@ -225,6 +226,7 @@ int MPI_Barrier(MPI_Comm comm)
     } else {
         while (__atomic_load_n(&g_hdr->barrier_sense, __ATOMIC_ACQUIRE) != g_local_sense) { progress(); relax(); }
     }
+    progress();
     return MPI_SUCCESS;
 }
 

@@ -246,3 +246,19 @@ def test_reference_async_program_runs_and_its_drift_is_reported(orc, tmp_path):
     drift = orc.check_metric(ref_av, av)
     print(f"reference async program, 4 ranks, {k} steps: av_vels drift vs SerialCode {drift:.3g} %")
     assert np.isfinite(drift) and np.all(np.isfinite(av)) and abs(drift) < 60.0
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 7])
+def test_minimpi_selfcheck(orc, tmp_path, nranks):
+    """The MPI stand-in on its own: ring exchange (also with P = 2, where both neighbours are the same rank and
+    only the tags separate the directions), un-waited receives, Sendrecv, a 12 MB message, Reduce."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "selfcheck"
+    subprocess.run(["/usr/bin/gcc", "-std=gnu11", "-O2", "-I", os.path.join(root, "oracle", "minimpi"),
+                    os.path.join(root, "tests", "data", "minimpi_selfcheck.c"), os.path.join(root, "oracle", "minimpi", "minimpi.c"),
+                    "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], env=dict(os.environ, MINIMPI_NP=str(nranks)), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"{nranks} ranks, 0 failures" in r.stdout
