@@ -456,3 +456,18 @@ def test_host_program_animation_frames(gpu, built, orc, tmp_path):
         _, _, u, _ = orc.final_state(p, cells, obst)
         assert lines[1:] == ["%.6E" % v for v in u.ravel()]
     assert not os.path.exists(tmp_path / "frames" / "animation_data" / "velocity_magnitude_000119.dat")
+
+
+def test_large_grid_with_partial_tiles_bit_exact(gpu, pkg, orc):
+    """A large grid whose width is not a multiple of the 128-cell tile and whose height is not a multiple of
+    the 16-row tile (partial TMA boxes in x and y, zero fill + masked stores), default kernels."""
+    nx, ny, iters = 4100, 3001, 6
+    obst = pkg.channel_obstacles(nx, ny, p=0.01, seed=3)
+    p = orc.Params(nx, ny, iters, 10, 0.1, 0.005, 1.85)
+    ref_cells, ref_av = orc.run_fused(p, obst, iters)
+    with pkg.Lattice(to_param(p), obst) as lat:
+        lat.run(iters)
+        cells, av = lat.cells(), lat.av_vels()
+    assert_lattice_equal(cells, ref_cells, obst)
+    tot, n = orc.tot_u_f64(p, ref_cells, obst)
+    assert av[-1] == pytest.approx(tot / n, rel=2e-6)
