@@ -118,3 +118,20 @@ def test_one_process_per_gpu_under_torchrun(ngpu, built, tmp_path):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = np.load(out)
     assert bool(res["cells_equal"]) and bool(res["av_equal"])
+
+
+@pytest.mark.parametrize("lag", [0, 2])
+def test_deterministic_stale_halo_on_real_gpus(ngpu, pkg, orc, lag):
+    """halo_lag on slabs that live on different GPUs (graph path: TMA interior kernel + boundary kernel with
+    flags over NVLink) against the oracle's decomposed run."""
+    p, obst = load_case(orc, "128x256")
+    iters = 200
+    n = 2
+    starts = pkg.partition(p.ny, n)
+    ref_cells, ref_av = orc.run_decomposed(p, obst, starts, lag, iters)
+    with pkg.Lattice(to_param(p), obst, ngpus=n, halo_lag=lag) as lat:
+        lat.run(iters)
+        cells, av = lat.cells(), lat.av_vels()
+    fluid = obst == 0
+    assert np.array_equal(bits(cells[fluid]), bits(ref_cells[fluid]))
+    np.testing.assert_allclose(av, ref_av, rtol=5e-5)
