@@ -18,9 +18,9 @@ SerialCode and OpenMP programs compiled from the sources where they lie).  Nothi
         serial_program      which binary produced the serial_* arrays
         reynolds            the "Reynolds number" line of its stdout
   tests/golden/steps_<grid>.npz
-        cells after 1, 2, 3, 10 steps + av_vels[0:10] from the SerialCode arithmetic, obtained by
-        running the SerialCode BINARY on a params file with maxIters=k -- only av_vels/final_state are
-        observable from the binary, so these hold (ux, uy, u, pressure) after k steps.
+        state after k = 1, 2, 3, 10, 101 steps (128x128 and 128x256), obtained by running the SerialCode
+        BINARY on a params file with maxIters=k -- only av_vels/final_state are observable from the
+        binary, so these hold (ux, uy, u, pressure) after k steps and av_vels[0:k].
 
 Usage:  python oracle/make_fixtures.py [--runs /tmp/ref_runs]   (re-uses finished runs in --runs)
 """
