@@ -153,6 +153,7 @@ def reference_arm(args) -> int:
     total_steps = args.steps + args.warmup
     rows = int(4.0e9 / (nx * max(total_steps, 1)))
     rows = max(64, min(2048, rows // 64 * 64))
+    rows = max(64, min(rows, (1 << 24) // nx))  # the reference formats 87 B of text per cell at the end: <= 16 M cells
     run_reference_cpu(nx, rows, max(args.warmup, 1), cores)  # warm-up run (page cache, CPU clocks)
     # every maintained variant of the reference on the same sample; the arm's value is the fastest one
     results = {}
