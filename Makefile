@@ -2,8 +2,10 @@
 #
 #   make            liblbm_b200.so (sm_100a CUDA + C ABI) and the d2q9-bgk host program
 #   make oracle     the CPU checker under oracle/ (test infrastructure; never linked into the product)
-#   make check      run d2q9-bgk on the shipped 128x128 case and compare with the golden fixture
-#                   (needs a GPU; the comparison is tests/check_outputs.py == check/check.py's rule)
+#   make check      run d2q9-bgk on the shipped 128x128 case and validate its files with the reference's own
+#                   check.py (tests/ref_check/check.py, byte for byte; SerialCode/Makefile:20-25).  Needs a GPU.
+#   make check-all  the same for all four shipped grids at their full iteration counts (LBM_ARITH=fast to
+#                   check the fast flavour)
 #   make clean
 #
 # nvcc cross-compiles for sm_100a without a GPU.
@@ -33,11 +35,23 @@ $(PKG)/gen_channel: $(PKG)/host/gen_channel.c
 oracle:
 	$(MAKE) -C oracle all ref
 
+GRIDS ?= 128x128 128x256 256x256 1024x1024
+
 check: all
-	cd build && ../$(BIN) ../tests/golden/inputs/input_128x128.params ../tests/golden/inputs/obstacles_128x128.dat \
-	  && python ../tests/check_outputs.py --golden ../tests/golden/128x128.npz --av-vels av_vels.dat --final-state final_state.dat
+	$(MAKE) check-all GRIDS=128x128
+
+check-all: all
+	@mkdir -p build/check/ref
+	python tests/ref_check/write_goldens.py build/check/ref $(GRIDS)
+	@set -e; for g in $(GRIDS); do \
+	  mkdir -p build/check/$$g; echo "== $$g =="; \
+	  (cd build/check/$$g && ../../../$(BIN) ../../../tests/golden/inputs/input_$$g.params ../../../tests/golden/inputs/obstacles_$$g.dat | grep -E 'Reynolds|Compute|B200'); \
+	  python tests/ref_check/check.py --ref-av-vels-file=build/check/ref/$$g.av_vels.dat \
+	    --ref-final-state-file=build/check/ref/$$g.final_state.dat \
+	    --av-vels-file=build/check/$$g/av_vels.dat --final-state-file=build/check/$$g/final_state.dat; \
+	done
 
 clean:
 	rm -rf build $(LIB) $(BIN) $(TOOLS)
 
-.PHONY: all oracle check clean
+.PHONY: all oracle check check-all clean

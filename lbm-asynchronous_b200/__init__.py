@@ -24,4 +24,5 @@ from .capi import (  # noqa: F401
     selftest,
 )
 from .lattice import Lattice, SlabLattice, av_from_sums  # noqa: F401
+from .inputs import check_metric, read_obstacles, read_params  # noqa: F401
 from .synthetic import channel_obstacles, channel_params  # noqa: F401

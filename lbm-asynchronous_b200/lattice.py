@@ -58,6 +58,7 @@ class Lattice:
         opt = _options(arith, halo_mode, halo_lag, use_graph, kernel, block)
         self._h = C.c_void_p()
         self._rows = param.ny
+        self._last_iters = 0
         if devices is not None:
             dev = (C.c_int * len(devices))(*devices)
             check(library().lbm_create_on(C.byref(param), _iptr(ob), len(devices), dev, C.byref(opt), C.byref(self._h)))
@@ -140,6 +141,12 @@ class Lattice:
         check(library().lbm_final_state(self._h, *[_fptr(o) for o in outs]))
         return tuple(outs)
 
+    def pressure(self) -> np.ndarray:
+        """Only the pressure column of final_state() (the one check.py compares), float32[rows, nx]."""
+        out = np.empty((self._rows, self.nx), dtype=np.float32)
+        check(library().lbm_final_state(self._h, None, None, None, _fptr(out)))
+        return out
+
     def cells(self) -> np.ndarray:
         """The lattice as the reference's AoS array, float32[rows, nx, 9]."""
         out = np.empty((self._rows, self.nx, capi.NSPEEDS), dtype=np.float32)
@@ -191,6 +198,7 @@ class SlabLattice(Lattice):
         ob = np.ascontiguousarray(obstacle_rows, dtype=np.int32).reshape(self._rows, param.nx)
         opt = _options(arith, halo_mode, halo_lag, use_graph, kernel, block)
         self._h = C.c_void_p()
+        self._last_iters = 0
         check(library().lbm_create_slab(C.byref(param), _iptr(ob), self.row0, self.row1, self.rank, self.nranks,
                                         int(device), C.byref(opt), C.byref(self._h)))
 

@@ -69,6 +69,16 @@ def combine_sums(sums: np.ndarray, nonfinite: np.ndarray, fluid_cells: int, grou
     return np.array([av_from_sums(lo_hi[i, 0], lo_hi[i, 1], bad[i], fluid) for i in range(n)], dtype=np.float32)
 
 
+def add_over_ranks(values: np.ndarray, group=None) -> np.ndarray:
+    """int64 all-reduce(SUM) of a small host array (the integer |u| sums, fluid-cell counts)."""
+    import torch
+
+    dist = _dist()
+    t = torch.from_numpy(np.ascontiguousarray(values, dtype=np.int64)).to(_device_for_collectives())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
 def gather_rows(rows: np.ndarray, starts, dst: int = 0, group=None):
     """Gather row slabs to rank `dst` in rank order (MPI/d2q9-bgk.c:265-295).  rows: float32[my_rows, ...].
     Returns the full array on `dst`, None elsewhere."""
@@ -117,6 +127,13 @@ class ShardedLattice:
     def av_vels(self) -> np.ndarray:
         sums, bad = self.slab.tot_u_sums()
         return combine_sums(sums, bad, self.slab.fluid_cells, self.group)
+
+    def tot_u_totals(self) -> np.ndarray:
+        """uint64[iters]: the exact integer |u| total (units of 2^-40, modulo 2^64) of every step of the last run,
+        added over the ranks -- equal, bit for bit, to what ONE GPU computes for the same grid."""
+        sums, _ = self.slab.tot_u_sums()
+        tot = add_over_ranks(sums, self.group).astype(np.uint64)
+        return tot[:, 0] + (tot[:, 1] << np.uint64(24))
 
     def final_state(self, dst: int = 0):
         parts = self.slab.final_state()
