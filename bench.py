@@ -255,6 +255,36 @@ def reference_arm(args) -> int:
     return 0
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Run this rank's host threads (and so its pinned allocations, first touch) on the NUMA node the GPU hangs
+    off: pinned buffers on the far socket cost the final-state download a hop over the inter-socket link.
+    Returns a short description, or None when the topology cannot be read."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return f"numa node {node}, {len(allowed)} cpus"
+    except Exception:
+        return None
+
+
 def workload_config(n_gpus: int, nx: int, ny: int | None, note: str | None = None):
     if n_gpus == 1:
         name = f"synthetic channel {nx}x{ny or 8192}, Bernoulli(0.005) obstacles, SplitMix64 seed 42 (BASELINE config 4)"
@@ -504,16 +534,20 @@ def main() -> int:
             st = pkg.partition(ny, n)
             r0, r1 = st[rank], st[rank + 1]
         my_cells = (r1 - r0) * nx
-        obst_pinned = torch.empty((r1 - r0, nx), dtype=torch.int32, pin_memory=True)
-        obst_pinned.numpy()[:] = pkg.channel_obstacles(nx, ny, row0=r0, row1=r1)
+        numa = bind_to_gpu_numa_node(local_rank)
+        # the obstacle map as the host program holds it: one bit per cell (lbm_create_packed / lbm_create_slab_packed)
+        words = (nx + 31) // 32
+        obst_pinned = torch.empty((r1 - r0, words), dtype=torch.int32, pin_memory=True)
+        obst_pinned.numpy().view(np.uint32)[:] = pkg.pack_obstacles(pkg.channel_obstacles(nx, ny, row0=r0, row1=r1))
+        obst_packed = obst_pinned.numpy().view(np.uint32)
         outs = [torch.empty((r1 - r0, nx), dtype=torch.float32, pin_memory=True) for _ in range(4)]
         barrier()
         t0 = time.perf_counter()
         if n == 1:
-            lat2 = pkg.Lattice(param, obst_pinned.numpy(), ngpus=1, **opts)
+            lat2 = pkg.Lattice(param, obst_packed, ngpus=1, **opts)
             run2 = lat2
         else:
-            run2 = ShardedLattice(param, lambda a, b: obst_pinned.numpy(), local_rank, **opts)
+            run2 = ShardedLattice(param, lambda a, b: obst_packed, local_rank, **opts)
             lat2 = run2.slab
         lat2.sync()
         t1 = time.perf_counter()
@@ -538,8 +572,9 @@ def main() -> int:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             secs = float(t.item())
         e2e = {"value": cells * K / secs / 1e6, "unit": "MLUPS",
-               "h2d_bytes_per_step": my_cells * 4 * n / K, "d2h_bytes_per_step": (my_cells * 16 * n + K * 8 * 3) / K,
-               "seconds": secs, "phases_s_rank0": phases, "what": "lbm_create(host obstacles) + lbm_run(K) + lbm_av_vels + lbm_final_state to pinned host"}
+               "h2d_bytes_per_step": (r1 - r0) * words * 4 * n / K, "d2h_bytes_per_step": (my_cells * 16 * n + K * 8 * 3) / K,
+               "seconds": secs, "phases_s_rank0": phases, "host_binding_rank0": numa,
+               "what": "lbm_create_packed(host obstacle bit map) + lbm_run(K) + lbm_av_vels + lbm_final_state to pinned host"}
         run2.close()
 
     if rank != 0:

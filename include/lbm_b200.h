@@ -99,6 +99,14 @@ int lbm_partition(int ny, int nslabs, int* starts);
 int lbm_create(const lbm_param_t* params, const int* obstacles, int ngpus, const lbm_options_t* opt,
                lbm_lattice_t** out);
 
+/* Same from a PACKED obstacle map: one bit per cell, row jj = lbm_packed_words_per_row(nx) 32-bit words, cell
+ * (ii, jj) is bit ii % 32 of word ii / 32 of row jj (bits beyond nx are ignored).  This is the device's own
+ * layout, so creation uploads 1/32 of the bytes of the int map and needs no packing pass.  Replaces the obstacle
+ * read + scatter of MPI/d2q9-bgk.c:730-829 (rank 0 reads the file into an int map and sends int slabs). */
+int lbm_create_packed(const lbm_param_t* params, const unsigned* obstacle_bits, int ngpus, const lbm_options_t* opt,
+                      lbm_lattice_t** out);
+size_t lbm_packed_words_per_row(int nx);
+
 /* Same, with an explicit device per slab: devices[i] is the CUDA device of slab i.  A device may be
  * named more than once (tests on a box with fewer GPUs than slabs): slabs that share a device run
  * one after the other on one stream, so the halo protocol is exercised without kernels that would
@@ -116,6 +124,9 @@ int lbm_create_on(const lbm_param_t* params, const int* obstacles, int nslabs, c
 #define LBM_HALO_HANDLE_BYTES 128
 int lbm_create_slab(const lbm_param_t* params, const int* obstacle_rows, int row0, int row1, int rank,
                     int nranks, int device, const lbm_options_t* opt, lbm_lattice_t** out);
+/* lbm_create_slab from this rank's rows of the packed map (see lbm_create_packed) */
+int lbm_create_slab_packed(const lbm_param_t* params, const unsigned* obstacle_bit_rows, int row0, int row1, int rank,
+                           int nranks, int device, const lbm_options_t* opt, lbm_lattice_t** out);
 int lbm_halo_export(lbm_lattice_t* lat, void* handle /* LBM_HALO_HANDLE_BYTES */);
 int lbm_halo_connect(lbm_lattice_t* lat, const void* south_handle /* rank-1 */, const void* north_handle /* rank+1 */);
 

@@ -23,6 +23,6 @@ from .capi import (  # noqa: F401
     partition,
     selftest,
 )
-from .lattice import Lattice, SlabLattice, av_from_sums  # noqa: F401
+from .lattice import Lattice, SlabLattice, av_from_sums, pack_obstacles  # noqa: F401
 from .inputs import check_metric, read_obstacles, read_params  # noqa: F401
 from .synthetic import channel_obstacles, channel_params  # noqa: F401

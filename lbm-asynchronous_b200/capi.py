@@ -18,7 +18,7 @@ OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, ETIMEOUT = 0, 1, 2, 3, 4, 5
 # every symbol include/lbm_b200.h declares (tests check the .so exports each of them)
 SYMBOLS = (
     "lbm_default_options", "lbm_last_error", "lbm_device_count", "lbm_partition", "lbm_create", "lbm_create_on",
-    "lbm_create_slab", "lbm_halo_export", "lbm_halo_connect", "lbm_set_stream", "lbm_run", "lbm_sync", "lbm_av_vels",
+    "lbm_create_packed", "lbm_packed_words_per_row", "lbm_create_slab", "lbm_create_slab_packed", "lbm_halo_export", "lbm_halo_connect", "lbm_set_stream", "lbm_run", "lbm_sync", "lbm_av_vels",
     "lbm_tot_u_sums", "lbm_av_from_sums", "lbm_fluid_cells", "lbm_steps_done", "lbm_av_velocity", "lbm_total_density",
     "lbm_final_state", "lbm_download_cells", "lbm_upload_cells", "lbm_last_run_ms", "lbm_kernel_launches",
     "lbm_num_slabs", "lbm_slab_info", "lbm_destroy", "lbm_selftest",
@@ -86,6 +86,9 @@ def library() -> C.CDLL:
         "lbm_create": (C.c_int, [pp, ip, C.c_int, op, C.POINTER(vp)]),
         "lbm_create_on": (C.c_int, [pp, ip, C.c_int, ip, op, C.POINTER(vp)]),
         "lbm_create_slab": (C.c_int, [pp, ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, op, C.POINTER(vp)]),
+        "lbm_create_packed": (C.c_int, [pp, C.POINTER(C.c_uint), C.c_int, op, C.POINTER(vp)]),
+        "lbm_packed_words_per_row": (C.c_size_t, [C.c_int]),
+        "lbm_create_slab_packed": (C.c_int, [pp, C.POINTER(C.c_uint), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, op, C.POINTER(vp)]),
         "lbm_halo_export": (C.c_int, [vp, vp]),
         "lbm_halo_connect": (C.c_int, [vp, vp, vp]),
         "lbm_set_stream": (C.c_int, [vp, vp]),

@@ -4,7 +4,8 @@
 // SerialCode/d2q9-bgk.c:531-543,610) and drives the sm_100a kernels of lbm_kernels.cuh:
 //   * lattices: 2 x 9 SoA planes per row slab, row pitch a multiple of 32 floats;
 //   * obstacles: 1 bit per cell;
-//   * the `for tt` loop (SerialCode:166-169) as CUDA graphs of GRAPH_STEPS kernel nodes, the step
+//   * the `for tt` loop (SerialCode:166-169) as CUDA graphs covering GRAPH_STEPS timesteps (16 launches of
+//     step2_kernel, which advances two steps per pass over HBM, or 32 single-step launches), the step
 //     index living in device memory so that one graph serves the whole run;
 //   * av_vels: exact integer sums of |u| per step kept on the device for the whole run, combined in
 //     a fixed way by the host afterwards (replaces the MPI_Reduce of MPI/d2q9-bgk.c:298-309);
@@ -15,6 +16,7 @@
 #include "../../include/lbm_b200.h"
 #include "lbm_kernels.cuh"
 #include "lbm_tma_kernel.cuh"
+#include "lbm_fused2_kernel.cuh"
 
 #include <cudaTypedefs.h>
 #include <unistd.h>
@@ -61,7 +63,7 @@ struct HaloHandle { // what lbm_halo_export writes (<= LBM_HALO_HANDLE_BYTES)
     int32_t device;
     int32_t pitch;
     int32_t ring;
-    int32_t pad;
+    int32_t config;     // everything both sides of a link must agree on (see halo_config_word)
     uint64_t local_ptr; // valid inside process `pid` only
     uint64_t bytes;
     cudaIpcMemHandle_t ipc;
@@ -77,13 +79,17 @@ struct Slab {
     uint32_t* obst = nullptr;           // rows x opitch
     unsigned long long* fluid_dev = nullptr;
     long long fluid = 0;
-    // halo block: [south ring][north ring][flags: 2 x 16 u64]  (one allocation: one IPC handle)
+    // halo block: [south ring][north ring][flags: 2 x 16 u64][obstacle bits of my row 0 and my last row]
+    // (one allocation: one IPC handle)
     char* halo_block = nullptr;
     size_t halo_bytes = 0;
     float* ring_s = nullptr;
     float* ring_n = nullptr;
     unsigned long long* flag_s = nullptr;
     unsigned long long* flag_n = nullptr;
+    uint32_t* edge_obst = nullptr;          // inside the halo block: [2][opitch], for the neighbours to copy
+    uint32_t* obst_halo = nullptr;          // [2][opitch]: the south neighbour's last row, the north neighbour's row 0
+    unsigned long long* arrive = nullptr;   // [2] last-arriver counters of halo_arrive()
     // the neighbours' sides facing me
     float* peer_ring_s = nullptr;           // south neighbour's north ring
     unsigned long long* peer_flag_s = nullptr;
@@ -116,6 +122,12 @@ struct Slab {
     CUtensorMap tmapw[2]; // per lattice: boxes TMA_TXW wide (x-shifted planes)
     int tma_ntx = 0, tma_ntiles = 0, tma_dq = 0, tma_dr = 0;
     unsigned tma_grid = 0;
+    // two timesteps per launch through step2_kernel
+    bool use_f2 = false;
+    CUtensorMap f2map[2];  // per lattice: boxes TMA_TX x SROWS
+    CUtensorMap f2mapw[2]; // per lattice: boxes TMA_TXW x SROWS
+    int f2_nsx = 0, f2_seg_h = 0, f2_nseg = 0, f2_nunits = 0;
+    unsigned f2_grid = 0;
 };
 
 } // namespace
@@ -127,11 +139,13 @@ struct lbm_lattice {
     int rank = 0, nranks = 1; // ring position of slab 0 / ring size (per-process mode), else 0 / nslabs
     bool per_process = false;
     bool connected = false;
+    bool poisoned = false;    // an lbm_run failed after it had started to queue work
     bool interleaved = false; // some slabs share a device (and therefore a stream): step-major launches only
     Slab* slabs = nullptr;
     int pitch = 0, opitch = 0, ring = 2;
     int cur = 0;             // which lattice holds the current state
     long long steps_done = 0;
+    long long epoch = 0;     // halo epochs done (every slab of the lattice counts the same sequence)
     long long launches = 0;
     long long run_first = 0; // absolute index of the first step of the last lbm_run
     int run_iters = 0;
@@ -143,6 +157,9 @@ struct lbm_lattice {
     void (*tma_kernel)(CUtensorMap, CUtensorMap, TmaArgs) = nullptr; // interior rows (null: `kernel` does every row)
     int tma_ty = 0, tma_stages = 0, tma_minb = 0, tma_resident = 0, sm_count = 0;
     int loop_resident[2] = {0, 0};
+    void (*f2_kernel)(CUtensorMap, CUtensorMap, Fused2Args) = nullptr; // pairs of steps (null: single steps only)
+    int f2_r = 0, f2_srows = 0, f2_stages = 0, f2_minb = 0, f2_resident = 0;
+    size_t f2_smem = 0;
     int prio_high = 0; // numerically lowest = most urgent stream / kernel-node priority of the device
     size_t tma_smem = 0;
 };
@@ -204,9 +221,37 @@ bool tma_by_shape(int ty, int stages, int minb, TmaChoice* c)
     return false;
 }
 
+typedef void (*f2_fn)(CUtensorMap, CUtensorMap, Fused2Args);
+struct F2Choice {
+    int r, srows, stages, minb;
+    f2_fn fn;
+};
+template <bool STRICT>
+bool f2_by_shape(int r, int srows, int stages, int minb, F2Choice* c)
+{
+#define LBM_F2_CASE(R_, S_, N_, M_)                                   \
+    if (r == R_ && srows == S_ && stages == N_ && minb == M_) {       \
+        *c = {R_, S_, N_, M_, step2_kernel<STRICT, R_, S_, N_, M_>};  \
+        return true;                                                  \
+    }
+    LBM_F2_CASE(8, 4, 3, 2)
+    LBM_F2_CASE(8, 4, 4, 1)
+    LBM_F2_CASE(8, 8, 2, 1)
+    LBM_F2_CASE(16, 8, 3, 1)
+    LBM_F2_CASE(16, 4, 6, 1)
+    LBM_F2_CASE(12, 4, 5, 1)
+#undef LBM_F2_CASE
+    return false;
+}
+
 // opt.kernel:
-//   0            library default: step_tma_kernel (TY 16, 2 stages, 1 CTA/SM) for the interior rows when nx % 4 == 0,
-//                nx >= 128 and the slab has >= 3 rows, step_vec4_kernel / step_scalar_kernel otherwise
+//   0            library default.  nx % 4 == 0, nx >= 128, every slab >= 8 rows, halo_lag == 0: step2_kernel, TWO
+//                timesteps per launch (8 consumer warps, stages of 4 rows, 3 stages, 2 CTAs/SM; an odd last step
+//                of a run takes the single-step kernels).  Otherwise single steps: step_tma_kernel (TY 16, 2
+//                stages, 1 CTA/SM) for the interior rows when nx % 4 == 0, nx >= 128 and the slab has >= 3 rows,
+//                step_vec4_kernel / step_scalar_kernel for the rest
+//   2RRSNM       step2_kernel with RR consumer warps (rows per iteration), S rows per stage, N stages, M CTAs per
+//                SM asked of the compiler (208432 208441 208821 216831 216461 212451)
 //   1TTSM        step_tma_kernel with TT rows per tile, S stages, M resident CTAs per SM asked of the compiler
 //                (10823 10822 10832 10831 10841 10434 10444 10443 10462 11621 11631)
 //   H M (10..39) step_vec4_kernel for every row: hint = H-1 (0 plain, 1 ld.nc.no_allocate, 2 + st.cs), min blocks M
@@ -223,6 +268,8 @@ struct KernelChoice {
     int hint, block, minb;
     bool tma;
     int tma_ty, tma_stages, tma_minb;
+    bool f2;
+    int f2_r, f2_srows, f2_stages, f2_minb;
 };
 KernelChoice choose_kernel(const lbm_options_t& o, int nx)
 {
@@ -240,7 +287,16 @@ KernelChoice choose_kernel(const lbm_options_t& o, int nx)
         k.tma_ty = 8, k.tma_stages = 4, k.tma_minb = 1;
     else
         k.tma_ty = 16, k.tma_stages = 2, k.tma_minb = 1;
-    if (o.kernel >= 10000) {
+    // pairs of steps: default wherever the TMA path applies; an explicit single-step variant (1TTSM, H M, 99)
+    // or a deterministic halo lag (defined per single step) switches it off
+    k.f2 = k.tma && (o.kernel == 0 || (o.kernel >= 200 && o.kernel <= 204) || o.kernel >= 200000) && o.halo_lag == 0;
+    k.f2_r = 8, k.f2_srows = 4, k.f2_stages = 3, k.f2_minb = 2;
+    if (o.kernel >= 200000) {
+        k.f2_r = (o.kernel - 200000) / 1000;
+        k.f2_srows = (o.kernel / 100) % 10;
+        k.f2_stages = (o.kernel / 10) % 10;
+        k.f2_minb = o.kernel % 10;
+    } else if (o.kernel >= 10000) {
         k.tma_ty = (o.kernel - 10000) / 100;
         k.tma_stages = (o.kernel / 10) % 10;
         k.tma_minb = o.kernel % 10;
@@ -362,20 +418,61 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
             s.tma_dr = static_cast<int>(s.tma_grid % s.tma_ntx);
         }
     }
+    // pairs of steps (step2_kernel): every slab of the lattice must take the same decision, so it depends on the
+    // nominal slab height only
+    s.use_f2 = s.use_tma && k.f2 && L->f2_kernel && (L->p.ny / total_slabs) >= 8 && s.rows >= 8;
+    if (s.use_f2) {
+        s.f2_nsx = (L->p.nx + F2_CORE - 1) / F2_CORE;
+        const int interior = s.rows - 4;
+        const long long g_max = static_cast<long long>(L->f2_resident) * L->sm_count;
+        // segment height: CTAs take units round-robin, so the launch lasts (units per CTA) x (iterations per unit,
+        // each R rows; the unit's two extra intermediate rows and ~half an iteration of pipeline fill included);
+        // pick the segment count that minimises it
+        int best_nseg = 1;
+        double best_cost = 1e300;
+        if (const char* e = getenv("LBM_F2_SEG")) {
+            const int h = atoi(e);
+            if (h > 0) best_nseg = (interior + h - 1) / h, best_cost = -1.0;
+        }
+        if (best_cost > 0.0) {
+            const int lo = std::max(1, interior / 640), hi = std::max(1, interior / 24);
+            for (int nseg = lo; nseg <= hi; nseg++) {
+                const int h = (interior + nseg - 1) / nseg;
+                const long long units = static_cast<long long>((interior + h - 1) / h) * s.f2_nsx;
+                const long long waves = (units + g_max - 1) / g_max;
+                const int iters = (h + 2 + L->f2_r - 1) / L->f2_r;
+                const double cost = static_cast<double>(waves) * (iters + 0.5);
+                if (cost < best_cost - 1e-9) best_cost = cost, best_nseg = nseg;
+            }
+        }
+        s.f2_seg_h = (interior + best_nseg - 1) / best_nseg;
+        s.f2_nseg = (interior + s.f2_seg_h - 1) / s.f2_seg_h;
+        const long long units = 2LL * s.f2_nsx + static_cast<long long>(s.f2_nseg) * s.f2_nsx;
+        if (units > 0x7fffffffLL) {
+            s.use_f2 = false;
+        } else {
+            s.f2_nunits = static_cast<int>(units);
+            s.f2_grid = static_cast<unsigned>(std::min<long long>(g_max, units));
+        }
+    }
+    if (getenv("LBM_DEBUG") && s.use_f2)
+        fprintf(stderr, "[lbm] slab rows %d..%d dev %d: step2_kernel R %d, %d rows/stage, %d stages, %d resident/SM, %zu B smem, grid %u, %d strips x %d segments of %d rows (+ %d boundary units)\n",
+                s.row0, s.row1 - 1, s.device, L->f2_r, L->f2_srows, L->f2_stages, L->f2_resident, L->f2_smem, s.f2_grid, s.f2_nsx, s.f2_nseg,
+                s.f2_seg_h, 2 * s.f2_nsx);
     if (getenv("LBM_DEBUG"))
         fprintf(stderr, "[lbm] slab rows %d..%d dev %d: %s, grid %u x %d thr, boundary grid %u; loop %d (%d cell/thread, grid %u, %d tiles); tma %d (TY %d, %d stages, %d CTA/SM wanted, %d resident, %zu B smem, grid %u, %d tiles)\n",
                 s.row0, s.row1 - 1, s.device, s.vec4 ? "vec4" : "scalar", s.grid, s.block, s.grid_b, s.use_loop ? 1 : 0, s.loop_vec, s.loop_grid,
                 s.loop_ntiles, s.use_tma ? 1 : 0, L->tma_ty,
                 L->tma_stages, L->tma_minb, L->tma_resident, L->tma_smem, s.tma_grid, s.tma_ntiles);
     // spread the per-step global atomics over several addresses when there are many CTAs
-    const unsigned ctas = s.use_tma ? s.tma_grid + s.grid_b : s.grid;
+    const unsigned ctas = s.use_tma ? std::max(s.tma_grid + s.grid_b, s.f2_grid) : s.grid;
     int slots = 1;
     while (slots < 64 && static_cast<unsigned>(slots) * 1024u < ctas) slots <<= 1;
     s.nslots = slots;
 }
 
-// the lattice as a 3-D tensor (x, y, plane) for the TMA unit; boxes are TMA_TX x TY x 1
-int make_tensor_maps(lbm_lattice* L, Slab& s)
+// the lattice as a 3-D tensor (x, y, plane) for the TMA unit; boxes are (TMA_TX | TMA_TXW) x box_rows x 1
+int encode_maps(lbm_lattice* L, Slab& s, int box_rows, CUtensorMap narrow[2], CUtensorMap wide[2])
 {
     static PFN_cuTensorMapEncodeTiled encode = nullptr;
     if (!encode) {
@@ -397,14 +494,21 @@ int make_tensor_maps(lbm_lattice* L, Slab& s)
                            : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : promo));
         }
         for (int w = 0; w < 2; w++) {
-            const cuuint32_t box[3] = {static_cast<cuuint32_t>(w ? TMA_TXW : TMA_TX), static_cast<cuuint32_t>(L->tma_ty), 1};
-            const CUresult r = encode(w ? &s.tmapw[i] : &s.tmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s.lat[i], gdim, gstride, box,
+            const cuuint32_t box[3] = {static_cast<cuuint32_t>(w ? TMA_TXW : TMA_TX), static_cast<cuuint32_t>(box_rows), 1};
+            const CUresult r = encode(w ? &wide[i] : &narrow[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s.lat[i], gdim, gstride, box,
                                       estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                       promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(LBM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
         }
     }
     return LBM_OK;
+}
+
+int make_tensor_maps(lbm_lattice* L, Slab& s)
+{
+    int rc = encode_maps(L, s, L->tma_ty, s.tmap, s.tmapw);
+    if (!rc && s.use_f2) rc = encode_maps(L, s, L->f2_srows, s.f2map, s.f2mapw);
+    return rc;
 }
 
 // LBM_DEBUG=1: wall-clock phases of lattice creation on stderr
@@ -427,7 +531,9 @@ struct DebugTimer {
     }
 };
 
-int alloc_slab(lbm_lattice* L, Slab& s, const int* obst_rows_host)
+// obst_rows_host: the slab's rows of the reference's int map (packed == false), or of the packed bit map
+// ([rows][opitch] words, bit x%32 of word x/32)
+int alloc_slab(lbm_lattice* L, Slab& s, const void* obst_rows_host, bool packed)
 {
     DebugTimer dbg;
     CU(cudaSetDevice(s.device));
@@ -456,13 +562,21 @@ int alloc_slab(lbm_lattice* L, Slab& s, const int* obst_rows_host)
     // packed to bits on the device, and the fluid cells counted
     {
         const size_t n = static_cast<size_t>(s.rows) * L->p.nx;
-        int* staging = reinterpret_cast<int*>(s.lat[1]);
         dbg.lap("small allocs");
-        CU(cudaMemcpyAsync(staging, obst_rows_host, n * sizeof(int), cudaMemcpyHostToDevice, s.stream));
-        const size_t warps = static_cast<size_t>(s.rows) * ((L->p.nx + 31) / 32);
-        const size_t blocks = std::min<size_t>((warps * 32 + 255) / 256, 148 * 16);
-        pack_obstacles_kernel<<<static_cast<unsigned>(blocks), 256, 0, s.stream>>>(staging, s.obst, L->p.nx, s.rows,
-                                                                                    L->opitch, s.fluid_dev);
+        if (packed) {
+            // already one bit per cell in the device's own layout (opitch == ceil(nx / 32) words per row)
+            const size_t nw = static_cast<size_t>(s.rows) * L->opitch;
+            CU(cudaMemcpyAsync(s.obst, obst_rows_host, nw * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+            const size_t blocks = std::min<size_t>((nw + 255) / 256, 148 * 8);
+            sanitize_obstacle_bits_kernel<<<static_cast<unsigned>(blocks), 256, 0, s.stream>>>(s.obst, L->p.nx, s.rows, L->opitch, s.fluid_dev);
+        } else {
+            int* staging = reinterpret_cast<int*>(s.lat[1]);
+            CU(cudaMemcpyAsync(staging, obst_rows_host, n * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+            const size_t warps = static_cast<size_t>(s.rows) * ((L->p.nx + 31) / 32);
+            const size_t blocks = std::min<size_t>((warps * 32 + 255) / 256, 148 * 16);
+            pack_obstacles_kernel<<<static_cast<unsigned>(blocks), 256, 0, s.stream>>>(staging, s.obst, L->p.nx, s.rows,
+                                                                                        L->opitch, s.fluid_dev);
+        }
         L->launches++;
         CU(cudaGetLastError());
         // initial state: every cell, obstacles included (SerialCode:551-567); both lattices
@@ -482,28 +596,40 @@ int alloc_slab(lbm_lattice* L, Slab& s, const int* obst_rows_host)
     return LBM_OK;
 }
 
+// floats in one halo ring of this lattice
+size_t ring_floats_of(const lbm_lattice* L) { return static_cast<size_t>(L->ring) * RING_ENTRIES * L->pitch; }
+
 int alloc_halo(lbm_lattice* L, Slab& s)
 {
     CU(cudaSetDevice(s.device));
-    const size_t ring_floats = static_cast<size_t>(L->ring) * 3 * L->pitch;
-    s.halo_bytes = 2 * ring_floats * sizeof(float) + 2 * 128;
+    const size_t ring_floats = ring_floats_of(L);
+    const size_t obst_bytes = 2 * static_cast<size_t>(L->opitch) * sizeof(uint32_t);
+    s.halo_bytes = 2 * ring_floats * sizeof(float) + 2 * 128 + obst_bytes;
     CU(cudaMalloc(&s.halo_block, s.halo_bytes));
     s.ring_s = reinterpret_cast<float*>(s.halo_block);
     s.ring_n = s.ring_s + ring_floats;
     s.flag_s = reinterpret_cast<unsigned long long*>(s.halo_block + 2 * ring_floats * sizeof(float));
     s.flag_n = s.flag_s + 16;
+    s.edge_obst = reinterpret_cast<uint32_t*>(s.halo_block + 2 * ring_floats * sizeof(float) + 256);
     CU(cudaMemsetAsync(s.flag_s, 0, 256, s.stream));
-    // both rings start in the uniform initial state (MPI_Testall_OptimizedVersion/d2q9-bgk.c:784-824):
-    // south ring holds planes 2,5,6; north ring planes 4,7,8
-    for (int slot = 0; slot < L->ring; slot++) {
-        float* rs = s.ring_s + static_cast<size_t>(slot) * 3 * L->pitch;
-        float* rn = s.ring_n + static_cast<size_t>(slot) * 3 * L->pitch;
-        fill_kernel<<<64, 256, 0, s.stream>>>(rs, L->pitch, L->w1);
-        fill_kernel<<<64, 256, 0, s.stream>>>(rs + L->pitch, 2 * static_cast<size_t>(L->pitch), L->w2);
-        fill_kernel<<<64, 256, 0, s.stream>>>(rn, L->pitch, L->w1);
-        fill_kernel<<<64, 256, 0, s.stream>>>(rn + L->pitch, 2 * static_cast<size_t>(L->pitch), L->w2);
-        L->launches += 4;
-    }
+    // obstacle bits of my first and last row, for the neighbours (they recompute those rows' intermediate step)
+    CU(cudaMemcpyAsync(s.edge_obst, s.obst, L->opitch * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s.stream));
+    CU(cudaMemcpyAsync(s.edge_obst + L->opitch, s.obst + static_cast<size_t>(s.rows - 1) * L->opitch, L->opitch * sizeof(uint32_t),
+                       cudaMemcpyDeviceToDevice, s.stream));
+    CU(cudaMalloc(&s.obst_halo, obst_bytes));
+    CU(cudaMemsetAsync(s.obst_halo, 0, obst_bytes, s.stream));
+    CU(cudaMalloc(&s.arrive, 2 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(s.arrive, 0, 2 * sizeof(unsigned long long), s.stream));
+    // both rings start in the uniform initial state (MPI_Testall_OptimizedVersion/d2q9-bgk.c:784-824): entries
+    // 0..2 hold planes 0,1,3; entries 3..5 and 6..8 the crossing planes (2,5,6 south ring / 4,7,8 north ring)
+    const float w[RING_ENTRIES] = {L->w0, L->w1, L->w1, L->w1, L->w2, L->w2, L->w1, L->w2, L->w2};
+    for (int slot = 0; slot < L->ring; slot++)
+        for (int e = 0; e < RING_ENTRIES; e++) {
+            const size_t off = (static_cast<size_t>(slot) * RING_ENTRIES + e) * L->pitch;
+            fill_kernel<<<64, 256, 0, s.stream>>>(s.ring_s + off, L->pitch, w[e]);
+            fill_kernel<<<64, 256, 0, s.stream>>>(s.ring_n + off, L->pitch, w[e]);
+            L->launches += 2;
+        }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s.stream));
     return LBM_OK;
@@ -530,14 +656,14 @@ HaloCfg make_halo_cfg(const lbm_lattice* L, const Slab& s)
     h.wait = (L->opt.halo_mode == LBM_HALO_SYNC) ? 1 : 0;
     h.ring = L->ring;
     h.lag = (L->opt.halo_mode == LBM_HALO_SYNC) ? L->opt.halo_lag : 0;
-    h.ctas_per_row = static_cast<unsigned>(s.use_loop ? s.loop_nbx : s.nbx);
-    h.slot_stride = 3ull * L->pitch;
+    h.arrive = s.arrive;
+    h.slot_stride = static_cast<unsigned long long>(RING_ENTRIES) * L->pitch;
     h.timeout_ns = L->timeout_ns;
     h.error = s.error;
     return h;
 }
 
-StepArgs make_args(const lbm_lattice* L, const Slab& s, int src, int step_offset)
+StepArgs make_args(const lbm_lattice* L, const Slab& s, int src, int step_offset, int epoch_offset)
 {
     StepArgs a;
     memset(&a, 0, sizeof a);
@@ -551,6 +677,7 @@ StepArgs make_args(const lbm_lattice* L, const Slab& s, int src, int step_offset
     a.sums_ref = s.sums_ref;
     a.nslots = s.nslots;
     a.step_offset = step_offset;
+    a.epoch_offset = epoch_offset;
     a.nx = L->p.nx, a.nxv = s.nxv, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
     a.tw_shift = s.tw_shift, a.nbx = s.nbx, a.ngroups = s.ngroups;
     a.accel_row = s.accel_row;
@@ -580,11 +707,32 @@ TmaArgs make_tma_args(const lbm_lattice* L, const Slab& s, int src, int step_off
     return a;
 }
 
+Fused2Args make_f2_args(const lbm_lattice* L, const Slab& s, int src, int step_offset, int epoch_offset)
+{
+    Fused2Args a;
+    memset(&a, 0, sizeof a);
+    a.in = s.lat[src];
+    a.out = s.lat[src ^ 1];
+    a.pf = plane_floats(L, s);
+    a.h = make_halo_cfg(L, s);
+    a.obst = s.obst;
+    a.obst_halo = s.obst_halo;
+    a.ctrl = s.ctrl;
+    a.sums_ref = s.sums_ref;
+    a.nslots = s.nslots;
+    a.step_offset = step_offset, a.epoch_offset = epoch_offset;
+    a.nx = L->p.nx, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
+    a.nsx = s.f2_nsx, a.seg_h = s.f2_seg_h, a.nseg = s.f2_nseg, a.nunits = s.f2_nunits;
+    a.accel_row = s.accel_row;
+    a.omega = L->p.omega, a.w1a = L->w1a, a.w2a = L->w2a;
+    return a;
+}
+
 // one timestep of one slab on its stream, outside a graph: the boundary rows (or every row), then
 // the interior rows
-int launch_step(lbm_lattice* L, Slab& s, int src, int step_offset)
+int launch_step(lbm_lattice* L, Slab& s, int src, int step_offset, int epoch_offset)
 {
-    const StepArgs a = make_args(L, s, src, step_offset);
+    const StepArgs a = make_args(L, s, src, step_offset, epoch_offset);
     L->kernel<<<s.use_tma ? s.grid_b : s.grid, s.block, 0, s.stream>>>(a);
     L->launches++;
     if (s.use_tma) {
@@ -596,19 +744,49 @@ int launch_step(lbm_lattice* L, Slab& s, int src, int step_offset)
     return LBM_OK;
 }
 
+// two timesteps of one slab in one launch of step2_kernel
+int launch_pair(lbm_lattice* L, Slab& s, int src, int step_offset, int epoch_offset)
+{
+    const Fused2Args a = make_f2_args(L, s, src, step_offset, epoch_offset);
+    L->f2_kernel<<<s.f2_grid, 32 * L->f2_r, L->f2_smem, s.stream>>>(s.f2map[src], s.f2mapw[src], a);
+    L->launches++;
+    CU(cudaGetLastError());
+    return LBM_OK;
+}
+
+// timesteps and halo epochs one step graph covers
+int graph_epochs(const Slab& s) { return s.use_f2 ? GRAPH_STEPS / 2 : GRAPH_STEPS; }
+
 int build_graph(lbm_lattice* L, Slab& s, int parity)
 {
     CU(cudaSetDevice(s.device));
     cudaGraph_t g;
     CU(cudaGraphCreate(&g, 0));
-    // per step: the boundary-row kernel (or the all-row kernel) and, beside it, the interior-row TMA
-    // kernel; both depend on both kernels of the previous step
     std::vector<cudaGraphNode_t> prev;
-    for (int j = 0; j < GRAPH_STEPS; j++) {
+    if (s.use_f2) {
+        // GRAPH_STEPS / 2 launches of step2_kernel, two timesteps each, one after the other
+        for (int j = 0; j < GRAPH_STEPS / 2; j++) {
+            const int src = (parity + j) & 1;
+            Fused2Args a = make_f2_args(L, s, src, 2 * j, j);
+            void* kp[3] = {&s.f2map[src], &s.f2mapw[src], &a};
+            cudaKernelNodeParams np = {};
+            np.func = reinterpret_cast<void*>(L->f2_kernel);
+            np.gridDim = dim3(s.f2_grid, 1, 1);
+            np.blockDim = dim3(32 * L->f2_r, 1, 1);
+            np.sharedMemBytes = static_cast<unsigned>(L->f2_smem);
+            np.kernelParams = kp;
+            cudaGraphNode_t node;
+            CU(cudaGraphAddKernelNode(&node, g, prev.data(), prev.size(), &np));
+            prev.assign(1, node);
+        }
+    }
+    // single steps -- per step: the boundary-row kernel (or the all-row kernel) and, beside it, the interior-row
+    // TMA kernel; both depend on both kernels of the previous step
+    for (int j = 0; j < GRAPH_STEPS && !s.use_f2; j++) {
         std::vector<cudaGraphNode_t> cur;
         const int src = (parity + j) & 1;
         {
-            StepArgs a = make_args(L, s, src, j);
+            StepArgs a = make_args(L, s, src, j, j);
             void* kp[1] = {&a};
             cudaKernelNodeParams np = {};
             np.func = reinterpret_cast<void*>(L->kernel);
@@ -644,8 +822,8 @@ int build_graph(lbm_lattice* L, Slab& s, int parity)
     }
     {
         int* ctrl = s.ctrl;
-        int by = GRAPH_STEPS;
-        void* kp[2] = {&ctrl, &by};
+        int by = GRAPH_STEPS, by_epochs = graph_epochs(s);
+        void* kp[3] = {&ctrl, &by, &by_epochs};
         cudaKernelNodeParams np = {};
         np.func = reinterpret_cast<void*>(advance_ctrl_kernel);
         np.gridDim = dim3(1, 1, 1);
@@ -798,6 +976,26 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
             if (i == 0 || sms < L->sm_count) L->sm_count = sms;
         }
     }
+    if (k.f2 && L->tma_kernel) {
+        F2Choice c;
+        const bool ok = strict ? f2_by_shape<true>(k.f2_r, k.f2_srows, k.f2_stages, k.f2_minb, &c)
+                               : f2_by_shape<false>(k.f2_r, k.f2_srows, k.f2_stages, k.f2_minb, &c);
+        if (!ok)
+            return fail(LBM_EINVAL, "no step2_kernel variant with %d consumer warps, %d rows per stage, %d stages, %d CTAs per SM", k.f2_r,
+                        k.f2_srows, k.f2_stages, k.f2_minb);
+        L->f2_kernel = c.fn;
+        L->f2_r = c.r, L->f2_srows = c.srows, L->f2_stages = c.stages, L->f2_minb = c.minb;
+        L->f2_smem = (static_cast<size_t>(c.stages) * stage_floats(c.srows) + static_cast<size_t>(c.r + 2) * F2_B2ROW) * sizeof(float) + 64;
+        for (int i = 0; i < L->nslabs; i++) {
+            CU(cudaSetDevice(L->slabs[i].device));
+            CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(c.fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(L->f2_smem)));
+            int resident = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, reinterpret_cast<const void*>(c.fn), 32 * c.r, L->f2_smem));
+            if (resident < 1) return fail(LBM_ECUDA, "step2_kernel does not fit on an SM (%zu bytes of shared memory)", L->f2_smem);
+            if (i == 0 || resident < L->f2_resident) L->f2_resident = resident;
+        }
+    }
     for (int i = 0; i < L->nslabs; i++) slab_geometry(L, L->slabs[i], k);
     return LBM_OK;
 }
@@ -812,6 +1010,8 @@ void free_slab(Slab& s)
     cudaFree(s.obst);
     cudaFree(s.fluid_dev);
     cudaFree(s.halo_block);
+    cudaFree(s.obst_halo);
+    cudaFree(s.arrive);
     cudaFree(s.ctrl);
     cudaFree(s.error);
     cudaFree(s.sums);
@@ -841,27 +1041,63 @@ int check_error_flags(lbm_lattice* L)
     return LBM_OK;
 }
 
-// push this slab's boundary rows of the current lattice into the neighbours' rings (every slot) and
-// set their flags to "everything up to steps_done delivered": used after lbm_upload_cells
+// push this slab's boundary rows of the current lattice into the neighbours' rings (every slot, all nine
+// entries) and set their flags to "every epoch so far delivered": used after lbm_upload_cells
 int push_boundary_rows(lbm_lattice* L, Slab& s)
 {
     CU(cudaSetDevice(s.device));
-    const size_t pf = plane_floats(L, s);
-    const float* base = s.lat[L->cur];
-    const int nx = L->p.nx;
-    const unsigned blocks = (nx + 255) / 256;
-    const size_t last = static_cast<size_t>(s.rows - 1) * L->pitch;
-    // my row 0 -> south neighbour's north ring: planes 4,7,8
-    push_row_kernel<<<blocks, 256, 0, s.stream>>>(base + 4 * pf, base + 7 * pf, base + 8 * pf, s.peer_ring_s, nx, L->pitch,
-                                                  L->ring, 3ull * L->pitch);
-    // my last row -> north neighbour's south ring: planes 2,5,6
-    push_row_kernel<<<blocks, 256, 0, s.stream>>>(base + 2 * pf + last, base + 5 * pf + last, base + 6 * pf + last,
-                                                  s.peer_ring_n, nx, L->pitch, L->ring, 3ull * L->pitch);
-    L->launches += 2;
+    RingFillArgs a;
+    a.lat = s.lat[L->cur];
+    a.pf = plane_floats(L, s);
+    a.ring_s = s.peer_ring_s, a.ring_n = s.peer_ring_n;
+    a.nx = L->p.nx, a.rows = s.rows, a.pitch = L->pitch, a.nring = L->ring;
+    a.slot_stride = static_cast<unsigned long long>(RING_ENTRIES) * L->pitch;
+    ring_fill_kernel<<<(L->p.nx + 255) / 256, 256, 0, s.stream>>>(a);
+    L->launches++;
     CU(cudaGetLastError());
-    const unsigned long long v = static_cast<unsigned long long>(L->steps_done) * static_cast<unsigned>(s.use_loop ? s.loop_nbx : s.nbx);
+    const unsigned long long v = static_cast<unsigned long long>(L->epoch);
     CU(cudaMemcpyAsync(s.peer_flag_s, &v, sizeof v, cudaMemcpyHostToDevice, s.stream));
     CU(cudaMemcpyAsync(s.peer_flag_n, &v, sizeof v, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    return LBM_OK;
+}
+
+// what both ends of a halo link must agree on, packed into the handle: arithmetic flavour, halo mode and lag,
+// and whether the lattice advances in pairs of steps (the epoch sequence differs)
+int32_t halo_config_word(const lbm_lattice* L)
+{
+    return static_cast<int32_t>((L->opt.arith & 0xf) | ((L->opt.halo_mode & 0xf) << 4) | ((L->opt.halo_lag & 0xff) << 8) |
+                                ((L->slabs[0].use_f2 ? 1 : 0) << 16) | ((L->slabs[0].use_loop ? 1 : 0) << 17));
+}
+
+// the halo protocol stores and adds into the neighbour device's memory from inside kernels: peer access is not
+// enough, the link must also carry native atomics (NVLink does; PCIe peers may not)
+int check_peer_link(int device, int peer)
+{
+    if (device == peer) return LBM_OK;
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, device, peer);
+    if (!can) return fail(LBM_ENODEVICE, "device %d cannot access device %d as a peer", device, peer);
+    int atomics = 0;
+    if (cudaDeviceGetP2PAttribute(&atomics, cudaDevP2PAttrNativeAtomicSupported, device, peer) != cudaSuccess) {
+        cudaGetLastError();
+        atomics = 0;
+    }
+    if (!atomics)
+        return fail(LBM_ENODEVICE, "device %d has no native peer atomics to device %d (the halo flags need them; NVLink provides them)",
+                    device, peer);
+    return LBM_OK;
+}
+
+// copy the obstacle bits of the neighbours' rows that touch this slab (step2_kernel recomputes those rows'
+// intermediate step): `south_edge` / `north_edge` point at the neighbours' edge_obst blocks ([2][opitch])
+int fetch_halo_obstacles(lbm_lattice* L, Slab& s, const uint32_t* south_edge, const uint32_t* north_edge)
+{
+    CU(cudaSetDevice(s.device));
+    const size_t row = static_cast<size_t>(L->opitch) * sizeof(uint32_t);
+    // the south neighbour's LAST row (second row of its block), the north neighbour's row 0 (first row of its block)
+    CU(cudaMemcpyAsync(s.obst_halo, south_edge + L->opitch, row, cudaMemcpyDefault, s.stream));
+    CU(cudaMemcpyAsync(s.obst_halo + L->opitch, north_edge, row, cudaMemcpyDefault, s.stream));
     CU(cudaStreamSynchronize(s.stream));
     return LBM_OK;
 }
@@ -918,8 +1154,8 @@ int lbm_partition(int ny, int nslabs, int* starts)
 }
 
 static int create_common(const lbm_param_t* params, const lbm_options_t* opt, int nslabs, const int* devices,
-                         const int* starts, const int* obstacles /* rows of slab 0 onwards, contiguous */, bool per_process,
-                         int rank, int nranks, lbm_lattice_t** out)
+                         const int* starts, const void* obstacles /* rows of slab 0 onwards, contiguous */, bool packed,
+                         bool per_process, int rank, int nranks, lbm_lattice_t** out)
 {
     if (!out) return fail(LBM_EINVAL, "out is NULL");
     *out = nullptr;
@@ -955,7 +1191,8 @@ static int create_common(const lbm_param_t* params, const lbm_options_t* opt, in
     rc = common_setup(L, params, opt);
     for (int i = 0; i < nslabs && !rc; i++) {
         Slab& s = L->slabs[i];
-        rc = alloc_slab(L, s, obstacles + static_cast<size_t>(s.row0 - starts[0]) * params->nx);
+        const size_t row_bytes = packed ? static_cast<size_t>(L->opitch) * sizeof(uint32_t) : static_cast<size_t>(params->nx) * sizeof(int);
+        rc = alloc_slab(L, s, static_cast<const char*>(obstacles) + static_cast<size_t>(s.row0 - starts[0]) * row_bytes, packed);
         if (!rc && s.use_tma) rc = make_tensor_maps(L, s);
         if (!rc && uses_halo(L)) rc = alloc_halo(L, s);
     }
@@ -970,8 +1207,8 @@ static int create_common(const lbm_param_t* params, const lbm_options_t* opt, in
     return LBM_OK;
 }
 
-int lbm_create_on(const lbm_param_t* params, const int* obstacles, int nslabs, const int* devices,
-                  const lbm_options_t* opt, lbm_lattice_t** out)
+static int create_on_impl(const lbm_param_t* params, const void* obstacles, bool packed, int nslabs, const int* devices,
+                          const lbm_options_t* opt, lbm_lattice_t** out)
 {
     if (nslabs < 1 || nslabs > 1024) return fail(LBM_EINVAL, "bad slab count %d", nslabs);
     if (!devices) return fail(LBM_EINVAL, "devices is NULL");
@@ -987,7 +1224,7 @@ int lbm_create_on(const lbm_param_t* params, const int* obstacles, int nslabs, c
     rc = lbm_partition(params->ny, nslabs, starts.data());
     if (rc) return rc;
     lbm_lattice_t* L = nullptr;
-    rc = create_common(params, opt, nslabs, devices, starts.data(), obstacles, false, 0, nslabs, &L);
+    rc = create_common(params, opt, nslabs, devices, starts.data(), obstacles, packed, false, 0, nslabs, &L);
     if (rc) return rc;
     if (nslabs > 1) {
         // slabs that share a device share a stream: their kernels then run one after the other in
@@ -1007,12 +1244,8 @@ int lbm_create_on(const lbm_param_t* params, const int* obstacles, int nslabs, c
             Slab& north = L->slabs[(i + 1) % nslabs];
             for (Slab* nb : {&south, &north}) {
                 if (nb->device == s.device) continue;
-                int can = 0;
-                cudaDeviceCanAccessPeer(&can, s.device, nb->device);
-                if (!can) {
-                    rc = fail(LBM_ENODEVICE, "device %d cannot access device %d as a peer", s.device, nb->device);
-                    break;
-                }
+                rc = check_peer_link(s.device, nb->device);
+                if (rc) break;
                 cudaSetDevice(s.device);
                 cudaError_t e = cudaDeviceEnablePeerAccess(nb->device, 0);
                 if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
@@ -1021,8 +1254,10 @@ int lbm_create_on(const lbm_param_t* params, const int* obstacles, int nslabs, c
                 }
                 cudaGetLastError();
             }
+            if (rc) break;
             s.peer_ring_s = south.ring_n, s.peer_flag_s = south.flag_n;
             s.peer_ring_n = north.ring_s, s.peer_flag_n = north.flag_s;
+            rc = fetch_halo_obstacles(L, s, south.edge_obst, north.edge_obst);
         }
         if (rc) {
             char keep[sizeof g_err];
@@ -1047,7 +1282,14 @@ int lbm_create_on(const lbm_param_t* params, const int* obstacles, int nslabs, c
     return LBM_OK;
 }
 
-int lbm_create(const lbm_param_t* params, const int* obstacles, int ngpus, const lbm_options_t* opt, lbm_lattice_t** out)
+int lbm_create_on(const lbm_param_t* params, const int* obstacles, int nslabs, const int* devices,
+                  const lbm_options_t* opt, lbm_lattice_t** out)
+{
+    return create_on_impl(params, obstacles, false, nslabs, devices, opt, out);
+}
+
+static int create_impl(const lbm_param_t* params, const void* obstacles, bool packed, int ngpus, const lbm_options_t* opt,
+                       lbm_lattice_t** out)
 {
     if (ngpus < 1) return fail(LBM_EINVAL, "ngpus must be >= 1, got %d", ngpus);
     int rc = check_device_available();
@@ -1056,11 +1298,24 @@ int lbm_create(const lbm_param_t* params, const int* obstacles, int ngpus, const
     if (ngpus > ndev) return fail(LBM_ENODEVICE, "%d GPUs requested but only %d CUDA device(s) are visible", ngpus, ndev);
     std::vector<int> devices(ngpus);
     for (int i = 0; i < ngpus; i++) devices[i] = i;
-    return lbm_create_on(params, obstacles, ngpus, devices.data(), opt, out);
+    return create_on_impl(params, obstacles, packed, ngpus, devices.data(), opt, out);
 }
 
-int lbm_create_slab(const lbm_param_t* params, const int* obstacle_rows, int row0, int row1, int rank, int nranks, int device,
-                    const lbm_options_t* opt, lbm_lattice_t** out)
+int lbm_create(const lbm_param_t* params, const int* obstacles, int ngpus, const lbm_options_t* opt, lbm_lattice_t** out)
+{
+    return create_impl(params, obstacles, false, ngpus, opt, out);
+}
+
+int lbm_create_packed(const lbm_param_t* params, const unsigned* obstacle_bits, int ngpus, const lbm_options_t* opt,
+                      lbm_lattice_t** out)
+{
+    return create_impl(params, obstacle_bits, true, ngpus, opt, out);
+}
+
+size_t lbm_packed_words_per_row(int nx) { return nx > 0 ? (static_cast<size_t>(nx) + 31) / 32 : 0; }
+
+static int create_slab_impl(const lbm_param_t* params, const void* obstacle_rows, bool packed, int row0, int row1, int rank, int nranks,
+                            int device, const lbm_options_t* opt, lbm_lattice_t** out)
 {
     int rc = validate_params(params);
     if (rc) return rc;
@@ -1074,7 +1329,19 @@ int lbm_create_slab(const lbm_param_t* params, const int* obstacle_rows, int row
     if (rc) return rc;
     if (device < 0 || device >= lbm_device_count()) return fail(LBM_ENODEVICE, "CUDA device %d is not visible", device);
     const int starts[2] = {row0, row1};
-    return create_common(params, opt, 1, &device, starts, obstacle_rows, true, rank, nranks, out);
+    return create_common(params, opt, 1, &device, starts, obstacle_rows, packed, true, rank, nranks, out);
+}
+
+int lbm_create_slab(const lbm_param_t* params, const int* obstacle_rows, int row0, int row1, int rank, int nranks, int device,
+                    const lbm_options_t* opt, lbm_lattice_t** out)
+{
+    return create_slab_impl(params, obstacle_rows, false, row0, row1, rank, nranks, device, opt, out);
+}
+
+int lbm_create_slab_packed(const lbm_param_t* params, const unsigned* obstacle_bit_rows, int row0, int row1, int rank, int nranks,
+                           int device, const lbm_options_t* opt, lbm_lattice_t** out)
+{
+    return create_slab_impl(params, obstacle_bit_rows, true, row0, row1, rank, nranks, device, opt, out);
 }
 
 int lbm_halo_export(lbm_lattice_t* L, void* handle)
@@ -1089,6 +1356,7 @@ int lbm_halo_export(lbm_lattice_t* L, void* handle)
     h.device = s.device;
     h.pitch = L->pitch;
     h.ring = L->ring;
+    h.config = halo_config_word(L);
     h.local_ptr = reinterpret_cast<uint64_t>(s.halo_block);
     h.bytes = s.halo_bytes;
     CU(cudaSetDevice(s.device));
@@ -1113,6 +1381,13 @@ int lbm_halo_connect(lbm_lattice_t* L, const void* south_handle, const void* nor
         if (h[i].magic != HANDLE_MAGIC) return fail(LBM_EINVAL, "neighbour handle %d is not a halo handle", i);
         if (h[i].pitch != L->pitch || h[i].ring != L->ring || h[i].bytes != s.halo_bytes)
             return fail(LBM_EINVAL, "neighbour %d was created with a different nx / halo_lag", i);
+        if (h[i].config != halo_config_word(L))
+            return fail(LBM_EINVAL, "neighbour %d was created with different options (arith / halo_mode / halo_lag / kernel): 0x%x vs 0x%x",
+                        i, h[i].config, halo_config_word(L));
+        if (h[i].device != s.device) {
+            int rc = check_peer_link(s.device, h[i].device);
+            if (rc) return rc;
+        }
         if (h[i].pid == static_cast<int32_t>(getpid())) {
             base[i] = reinterpret_cast<char*>(h[i].local_ptr); // same process (e.g. a ring of one)
             if (h[i].device != s.device) {
@@ -1133,7 +1408,7 @@ int lbm_halo_connect(lbm_lattice_t* L, const void* south_handle, const void* nor
             base[i] = static_cast<char*>(p);
         }
     }
-    const size_t ring_floats = static_cast<size_t>(L->ring) * 3 * L->pitch;
+    const size_t ring_floats = ring_floats_of(L);
     auto ring_s_of = [&](char* b) { return reinterpret_cast<float*>(b); };
     auto ring_n_of = [&](char* b) { return reinterpret_cast<float*>(b) + ring_floats; };
     auto flag_s_of = [&](char* b) { return reinterpret_cast<unsigned long long*>(b + 2 * ring_floats * sizeof(float)); };
@@ -1141,6 +1416,9 @@ int lbm_halo_connect(lbm_lattice_t* L, const void* south_handle, const void* nor
     // my south neighbour receives my row 0 in ITS north ring; my north neighbour my last row in ITS south ring
     s.peer_ring_s = ring_n_of(base[0]), s.peer_flag_s = flag_n_of(base[0]);
     s.peer_ring_n = ring_s_of(base[1]), s.peer_flag_n = flag_s_of(base[1]);
+    auto edge_obst_of = [&](char* b) { return reinterpret_cast<const uint32_t*>(b + 2 * ring_floats * sizeof(float) + 256); };
+    int rc = fetch_halo_obstacles(L, s, edge_obst_of(base[0]), edge_obst_of(base[1]));
+    if (rc) return rc;
     L->connected = true;
     return prepare_graphs(L);
 }
@@ -1164,15 +1442,50 @@ int lbm_run(lbm_lattice_t* L, int iters)
     if (iters < 0) return fail(LBM_EINVAL, "iters must be >= 0");
     if (!L->connected) return fail(LBM_EINVAL, "lbm_halo_connect has not been called");
     if (L->steps_done + iters > 0x7ffffff0LL) return fail(LBM_EINVAL, "step counter would overflow");
-    L->run_first = L->steps_done;
-    L->run_iters = iters;
-    if (iters == 0) return LBM_OK;
+    if (L->poisoned) return fail(LBM_ECUDA, "an earlier lbm_run failed half-way: the slabs are no longer at the same step");
+    if (iters == 0) {
+        L->run_first = L->steps_done;
+        L->run_iters = 0;
+        return LBM_OK;
+    }
     const int first = static_cast<int>(L->steps_done);
+    const int parity = L->cur;
+    const bool use_graphs = L->opt.use_graph && !L->interleaved;
+    bool all_loop = true, f2 = true;
+    for (int i = 0; i < L->nslabs; i++) all_loop = all_loop && L->slabs[i].use_loop, f2 = f2 && L->slabs[i].use_f2;
+    // everything that can fail without having touched the lattice comes first: a failure here leaves the run
+    // un-started and the call can be repeated
     for (int i = 0; i < L->nslabs; i++) {
         Slab& s = L->slabs[i];
         int rc = ensure_sums(L, s, static_cast<size_t>(iters));
         if (rc) return rc;
-        set_ctrl_kernel<<<1, 32, 0, s.stream>>>(s.ctrl, first, first, first + iters - 1);
+        if (use_graphs && !all_loop && iters >= GRAPH_STEPS && !s.graph[parity]) {
+            rc = build_graph(L, s, parity);
+            if (rc) return rc;
+        }
+    }
+    // from here on a failure leaves slabs at different steps (or the driven row accelerated twice on a retry)
+    struct Poison {
+        lbm_lattice* L;
+        bool armed = true;
+        ~Poison()
+        {
+            if (armed) L->poisoned = true;
+        }
+    } poison{L};
+    L->run_first = L->steps_done;
+    L->run_iters = iters;
+
+    // lattices that advance in pairs of steps re-deliver their boundary rows at the start of every run (halo
+    // epoch e0): the accelerate_flow() pre-pass below changes row ny-2, which the first slab reads as its far
+    // south halo row, after the previous run's last step delivered it
+    const bool start_push = f2 && uses_halo(L);
+    const long long e0 = L->epoch;
+    const int epoch_base = static_cast<int>(e0 + (start_push ? 1 : 0)); // epoch of the first step kernel
+    for (int i = 0; i < L->nslabs; i++) {
+        Slab& s = L->slabs[i];
+        CU(cudaSetDevice(s.device));
+        set_ctrl_kernel<<<1, 32, 0, s.stream>>>(s.ctrl, first, first, first + iters - 1, epoch_base);
         L->launches++;
         if (i == 0) CU(cudaEventRecord(s.ev0, s.stream));
         // accelerate_flow() of the first step (SerialCode:209); every later step's is applied by the
@@ -1190,10 +1503,26 @@ int lbm_run(lbm_lattice_t* L, int iters)
         }
         CU(cudaGetLastError());
     }
-    int done = 0;
-    const int parity = L->cur;
-    bool all_loop = true;
-    for (int i = 0; i < L->nslabs; i++) all_loop = all_loop && L->slabs[i].use_loop;
+    if (start_push) {
+        for (int i = 0; i < L->nslabs; i++) {
+            Slab& s = L->slabs[i];
+            CU(cudaSetDevice(s.device));
+            HaloPushArgs pa;
+            memset(&pa, 0, sizeof pa);
+            pa.lat = s.lat[L->cur];
+            pa.pf = plane_floats(L, s);
+            pa.h = make_halo_cfg(L, s);
+            pa.ctrl = s.ctrl;
+            pa.epoch_offset = -1;
+            pa.nx = L->p.nx, pa.rows = s.rows, pa.pitch = L->pitch;
+            halo_push_kernel<<<(L->p.nx / 4 + 127) / 128, 128, 0, s.stream>>>(pa);
+            L->launches++;
+            CU(cudaGetLastError());
+        }
+    }
+    int done = 0;        // timesteps queued
+    long long passes = 0; // lattice swaps queued
+    long long epochs = 0; // halo epochs queued after epoch_base
     if (all_loop) {
         // every step of this run in cooperative launches of step_loop_kernel, one per slab (slabs on different
         // GPUs run at the same time and exchange halo rows and flags); more than one launch per slab only if
@@ -1215,6 +1544,7 @@ int lbm_run(lbm_lattice_t* L, int iters)
                 a.barrier = s.loop_barrier;
                 a.nslots = s.nslots;
                 a.first_step = first + done, a.nsteps = n, a.last_step = first + iters - 1;
+                a.first_epoch = epoch_base + done;
                 a.src = (parity + done) & 1;
                 a.nx = L->p.nx, a.nxv = s.loop_nxv, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
                 a.tw_shift = s.loop_tw_shift, a.nbx = s.loop_nbx, a.nby = s.loop_nby, a.ntiles = s.loop_ntiles;
@@ -1231,19 +1561,17 @@ int lbm_run(lbm_lattice_t* L, int iters)
                 L->launches++;
             }
             done += n;
+            passes += n;
+            epochs += n;
         }
     }
-    if (L->opt.use_graph && !L->interleaved) {
+    if (use_graphs && !all_loop) {
         while (iters - done >= GRAPH_STEPS) {
             for (int i = 0; i < L->nslabs; i++) {
                 Slab& s = L->slabs[i];
-                if (!s.graph[parity]) {
-                    int rc = build_graph(L, s, parity);
-                    if (rc) return rc;
-                }
                 CU(cudaSetDevice(s.device));
                 CU(cudaGraphLaunch(s.graph[parity], s.stream));
-                L->launches += GRAPH_STEPS * (s.use_tma ? 2 : 1) + 1;
+                L->launches += (s.use_f2 ? GRAPH_STEPS / 2 : GRAPH_STEPS * (s.use_tma ? 2 : 1)) + 1;
                 if (i == 0 && getenv("LBM_DEBUG") && s.dbg_events.size() < 256) {
                     cudaEvent_t e;
                     CU(cudaEventCreate(&e));
@@ -1252,25 +1580,41 @@ int lbm_run(lbm_lattice_t* L, int iters)
                 }
             }
             done += GRAPH_STEPS;
+            passes += f2 ? GRAPH_STEPS / 2 : GRAPH_STEPS; // even: the graph's source lattice is `parity` again
+            epochs += f2 ? GRAPH_STEPS / 2 : GRAPH_STEPS;
         }
     }
-    const int rest = iters - done; // parity of `done` is even, so the source lattice is still `parity`
-    for (int j = 0; j < rest; j++) {
+    // what is left (or everything, without graphs): plain launches, slabs interleaved pass by pass.  The ctrl words
+    // already point at step `first + done` / epoch `epoch_base + epochs` (the graphs advance them).
+    const int rest = iters - done;
+    int rest_epochs = 0;
+    if (rest > 0) {
+        const int pairs = f2 ? rest / 2 : 0;
+        for (int j = 0; j < pairs; j++)
+            for (int i = 0; i < L->nslabs; i++) {
+                Slab& s = L->slabs[i];
+                CU(cudaSetDevice(s.device));
+                int rc = launch_pair(L, s, static_cast<int>((parity + passes + j) & 1), 2 * j, j);
+                if (rc) return rc;
+            }
+        const int singles = rest - 2 * pairs;
+        for (int j = 0; j < singles; j++)
+            for (int i = 0; i < L->nslabs; i++) {
+                Slab& s = L->slabs[i];
+                CU(cudaSetDevice(s.device));
+                int rc = launch_step(L, s, static_cast<int>((parity + passes + pairs + j) & 1), 2 * pairs + j, pairs + j);
+                if (rc) return rc;
+            }
+        rest_epochs = pairs + singles;
+        passes += rest_epochs;
+        epochs += rest_epochs;
         for (int i = 0; i < L->nslabs; i++) {
             Slab& s = L->slabs[i];
             CU(cudaSetDevice(s.device));
-            int rc = launch_step(L, s, (parity + j) & 1, j);
-            if (rc) return rc;
-        }
-    }
-    for (int i = 0; i < L->nslabs; i++) {
-        Slab& s = L->slabs[i];
-        CU(cudaSetDevice(s.device));
-        if (rest) {
-            advance_ctrl_kernel<<<1, 32, 0, s.stream>>>(s.ctrl, rest);
+            advance_ctrl_kernel<<<1, 32, 0, s.stream>>>(s.ctrl, rest, rest_epochs);
             L->launches++;
+            CU(cudaGetLastError());
         }
-        CU(cudaGetLastError());
     }
     // slab 0's stop event is recorded after it has seen every other slab's stream finish
     for (int i = 1; i < L->nslabs; i++) {
@@ -1284,7 +1628,9 @@ int lbm_run(lbm_lattice_t* L, int iters)
     CU(cudaSetDevice(L->slabs[0].device));
     CU(cudaEventRecord(L->slabs[0].ev1, L->slabs[0].stream));
     L->steps_done += iters;
-    L->cur = (parity + iters) & 1;
+    L->epoch = epoch_base + epochs;
+    L->cur = static_cast<int>((parity + passes) & 1);
+    poison.armed = false;
     return LBM_OK;
 }
 
@@ -1301,7 +1647,7 @@ int lbm_sync(lbm_lattice_t* L)
 
 int lbm_tot_u_sums(lbm_lattice_t* L, long long* sums, long long* nonfinite, int iters)
 {
-    if (!L || !sums) return fail(LBM_EINVAL, "NULL argument");
+    if (!L || (!sums && iters != 0)) return fail(LBM_EINVAL, "NULL argument");
     if (iters < 0 || iters > L->run_iters) return fail(LBM_EINVAL, "the last lbm_run call made %d steps, %d asked for", L->run_iters, iters);
     int rc = lbm_sync(L);
     if (rc) return rc;
@@ -1354,9 +1700,10 @@ long long lbm_steps_done(const lbm_lattice_t* L) { return L ? L->steps_done : 0;
 
 int lbm_av_vels(lbm_lattice_t* L, float* av_vels, int iters)
 {
-    if (!L || !av_vels) return fail(LBM_EINVAL, "NULL argument");
+    if (!L || (!av_vels && iters != 0)) return fail(LBM_EINVAL, "NULL argument");
     if (L->per_process && L->nranks > 1)
         return fail(LBM_EINVAL, "one slab per process: add lbm_tot_u_sums over the ranks and use lbm_av_from_sums");
+    if (iters == 0) return LBM_OK; // maxIters = 0: the reference writes an empty av_vels.dat
     std::vector<long long> sums(2 * static_cast<size_t>(iters > 0 ? iters : 0)), bad(iters > 0 ? iters : 0);
     int rc = lbm_tot_u_sums(L, sums.data(), bad.data(), iters);
     if (rc) return rc;

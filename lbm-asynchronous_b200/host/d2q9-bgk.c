@@ -20,15 +20,20 @@
  *   LBM_ARITH=strict|fast    collision arithmetic (default strict: bit-identical to SerialCode)
  *   LBM_SKIP_FINAL_STATE=1   do not write final_state.dat (87 bytes per cell of text)
  *   LBM_KERNEL, LBM_BLOCK    kernel variant / CTA size (tuning)
+ *   LBM_PARSE_ONLY=1         read both input files, print the number of blocked cells, an FNV-1a hash of the packed
+ *                            obstacle map and the time the parse took, and exit (no GPU needed; for tooling/tests)
  *   LBM_ANIMATION_EVERY=N    write animation_data/velocity_magnitude_%06d.dat after every N-th timestep
  *                            (tt = 0, N, 2N, ...), the frames Visualization/animation.py reads.  Off by
  *                            default: the reference ships with these calls commented out
  *                            (SerialCode/d2q9-bgk.c:171-173, write_animation_data :802-849)
  */
+#include <fcntl.h>
 #include <pthread.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/time.h>
 #include <unistd.h>
@@ -99,28 +104,195 @@ static void read_params(const char* path, lbm_param_t* p)
     fclose(fp);
 }
 
-/* obstacle file: lines `x y 1` until EOF; same checks and messages as SerialCode:588-601 */
-static int* read_obstacles(const char* path, const lbm_param_t* p)
+/* ---- obstacle file -> packed bit map --------------------------------------------------------------------
+ * The reference reads the file with  while ((retval = fscanf(fp, "%d %d %d\n", &xx, &yy, &blocked)) != EOF)
+ * (SerialCode/d2q9-bgk.c:588-601): a stream of whitespace-separated integers taken three at a time, four checks
+ * per triple, the first failing triple (in file order) ends the program.  One fscanf per line on one core takes
+ * ~1 s per 3 M lines; the 32768 x 32768 synthetic channel has 5.4 M.  Same semantics here, but the file is
+ * mapped and tokenised by all host cores: pass 1 counts the integer tokens of each chunk (and finds the first
+ * byte that is not part of an integer), a prefix sum tells each chunk where its first triple starts, pass 2
+ * checks the triples and sets bits.  The map is 1 bit per cell (what the device keeps) instead of the reference's
+ * int per cell. */
+typedef struct {
+    const char* base;
+    size_t begin, end, size; /* this chunk: [begin, end) of [0, size) */
+    int nx, ny;
+    uint32_t* bits;
+    size_t words_per_row;
+    /* pass 1 */
+    size_t ntokens;
+    size_t garbage; /* offset of the first byte that starts no integer, or SIZE_MAX */
+    /* pass 2 */
+    size_t first_token; /* global index of this chunk's first token */
+    size_t total_tokens; /* tokens before the first garbage byte of the whole file */
+    size_t err_triple;  /* first failing triple, or SIZE_MAX */
+    int err_kind;       /* 1 x range, 2 y range, 3 blocked value */
+} obst_job;
+
+static int is_space(char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
+
+/* one "%d" conversion at *pos: skips white space, then [+-]digits.  1: value stored; 0: not an integer
+ * (*pos = the offending byte); -1: only white space left before `limit` */
+static int scan_int(const char* s, size_t* pos, size_t limit, long long* value)
 {
-    const size_t n = (size_t)p->nx * (size_t)p->ny;
-    int* obstacles = calloc(n, sizeof(int));
-    if (!obstacles) DIE("cannot allocate column memory for obstacles");
-    FILE* fp = fopen(path, "r");
-    if (!fp) {
+    size_t p = *pos;
+    while (p < limit && is_space(s[p])) p++;
+    if (p >= limit) {
+        *pos = p;
+        return -1;
+    }
+    size_t q = p;
+    int neg = 0;
+    if (s[q] == '+' || s[q] == '-') neg = s[q] == '-', q++;
+    if (q >= limit || s[q] < '0' || s[q] > '9') {
+        *pos = p;
+        return 0;
+    }
+    long long v = 0;
+    while (q < limit && s[q] >= '0' && s[q] <= '9') {
+        if (v < (1LL << 40)) v = v * 10 + (s[q] - '0');
+        q++;
+    }
+    *value = neg ? -v : v;
+    *pos = q;
+    return 1;
+}
+
+static void* obst_pass1(void* arg)
+{
+    obst_job* j = (obst_job*)arg;
+    size_t p = j->begin, n = 0;
+    j->garbage = SIZE_MAX;
+    for (;;) {
+        /* a token belongs to the chunk its first byte lies in; tokens never contain white space and chunks are
+         * cut at white space, so scanning up to the end of the file never reads a token twice */
+        size_t q = p;
+        while (q < j->end && is_space(j->base[q])) q++;
+        if (q >= j->end) break;
+        long long v;
+        p = q;
+        const int r = scan_int(j->base, &p, j->size, &v);
+        if (r != 1) {
+            j->garbage = q;
+            break;
+        }
+        n++;
+    }
+    j->ntokens = n;
+    return NULL;
+}
+
+static void* obst_pass2(void* arg)
+{
+    obst_job* j = (obst_job*)arg;
+    j->err_triple = SIZE_MAX;
+    j->err_kind = 0;
+    size_t p = j->begin;
+    size_t tok = j->first_token;
+    /* skip the tail of a triple that started in an earlier chunk */
+    long long v;
+    while (tok % 3 != 0 && tok < j->first_token + j->ntokens) {
+        scan_int(j->base, &p, j->size, &v);
+        tok++;
+    }
+    while (tok < j->first_token + j->ntokens && tok + 3 <= j->total_tokens) {
+        long long t[3];
+        for (int i = 0; i < 3; i++) scan_int(j->base, &p, j->size, &t[i]); /* may run into the next chunk */
+        const size_t triple = tok / 3;
+        int kind = 0;
+        if (t[0] < 0 || t[0] > j->nx - 1) kind = 1;
+        else if (t[1] < 0 || t[1] > j->ny - 1) kind = 2;
+        else if (t[2] != 1) kind = 3;
+        if (kind) {
+            j->err_triple = triple;
+            j->err_kind = kind;
+            return NULL;
+        }
+        __atomic_fetch_or(&j->bits[(size_t)t[1] * j->words_per_row + ((size_t)t[0] >> 5)], 1u << (t[0] & 31), __ATOMIC_RELAXED);
+        tok += 3;
+    }
+    return NULL;
+}
+
+static uint32_t* read_obstacles(const char* path, const lbm_param_t* p)
+{
+    const size_t wpr = ((size_t)p->nx + 31) / 32;
+    uint32_t* bits = calloc(wpr * (size_t)p->ny, sizeof(uint32_t));
+    if (!bits) DIE("cannot allocate column memory for obstacles");
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) {
         char msg[1024];
         snprintf(msg, sizeof msg, "could not open input obstacles file: %s", path);
         DIE(msg);
     }
-    int xx, yy, blocked, got;
-    while ((got = fscanf(fp, "%d %d %d\n", &xx, &yy, &blocked)) != EOF) {
-        if (got != 3) DIE("expected 3 values per line in obstacle file");
-        if (xx < 0 || xx > p->nx - 1) DIE("obstacle x-coord out of range");
-        if (yy < 0 || yy > p->ny - 1) DIE("obstacle y-coord out of range");
-        if (blocked != 1) DIE("obstacle blocked value should be 1");
-        obstacles[(size_t)xx + (size_t)yy * p->nx] = blocked;
+    struct stat st;
+    if (fstat(fd, &st) != 0) DIE("could not open input obstacles file");
+    const size_t size = (size_t)st.st_size;
+    if (size == 0) {
+        close(fd);
+        return bits;
     }
-    fclose(fp);
-    return obstacles;
+    const char* base = mmap(NULL, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (base == MAP_FAILED) DIE("could not map the obstacles file");
+    long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+    int nthreads = (int)(ncpu < 1 ? 1 : (ncpu > 64 ? 64 : ncpu));
+    if (size < (size_t)nthreads * 65536) nthreads = (int)(size / 65536) + 1;
+    obst_job* jobs = calloc((size_t)nthreads, sizeof *jobs);
+    pthread_t* tids = calloc((size_t)nthreads, sizeof *tids);
+    if (!jobs || !tids) DIE("cannot allocate memory for the input threads");
+    size_t cut = 0;
+    for (int i = 0; i < nthreads; i++) {
+        size_t end = (i == nthreads - 1) ? size : size / (size_t)nthreads * (size_t)(i + 1);
+        if (end < cut) end = cut;
+        while (end < size && !is_space(base[end])) end++; /* never inside a token */
+        obst_job j = {base, cut, end, size, p->nx, p->ny, bits, wpr, 0, SIZE_MAX, 0, 0, SIZE_MAX, 0};
+        jobs[i] = j;
+        cut = end;
+    }
+    for (int pass = 1; pass <= 2; pass++) {
+        for (int i = 0; i < nthreads; i++)
+            if (pthread_create(&tids[i], NULL, pass == 1 ? obst_pass1 : obst_pass2, &jobs[i]) != 0) {
+                (pass == 1 ? obst_pass1 : obst_pass2)(&jobs[i]);
+                tids[i] = 0;
+            }
+        for (int i = 0; i < nthreads; i++)
+            if (tids[i]) pthread_join(tids[i], NULL);
+        if (pass == 1) {
+            /* tokens before the first byte that is not part of an integer: all the reference would ever convert */
+            size_t total = 0;
+            int stopped = 0;
+            for (int i = 0; i < nthreads; i++) {
+                jobs[i].first_token = total;
+                if (stopped) jobs[i].ntokens = 0;
+                total += jobs[i].ntokens;
+                if (jobs[i].garbage != SIZE_MAX) stopped = 1;
+            }
+            for (int i = 0; i < nthreads; i++) jobs[i].total_tokens = total;
+        }
+    }
+    size_t total = jobs[0].total_tokens;
+    int stopped = 0;
+    for (int i = 0; i < nthreads; i++) stopped |= jobs[i].garbage != SIZE_MAX;
+    size_t err_triple = SIZE_MAX;
+    int err_kind = 0;
+    for (int i = 0; i < nthreads; i++)
+        if (jobs[i].err_triple < err_triple) err_triple = jobs[i].err_triple, err_kind = jobs[i].err_kind;
+    munmap((void*)base, size);
+    close(fd);
+    free(jobs);
+    free(tids);
+    /* the first failing triple in file order; an incomplete last triple (or a non-integer) comes after every
+     * complete one */
+    if (err_kind == 1) DIE("obstacle x-coord out of range");
+    if (err_kind == 2) DIE("obstacle y-coord out of range");
+    if (err_kind == 3) DIE("obstacle blocked value should be 1");
+    if (stopped || total % 3 != 0) DIE("expected 3 values per line in obstacle file");
+    return bits;
+}
+
+static int obstacle_at(const uint32_t* bits, size_t words_per_row, int ii, int jj)
+{
+    return (int)((bits[(size_t)jj * words_per_row + ((size_t)ii >> 5)] >> (ii & 31)) & 1u);
 }
 
 /* final_state.dat: `ii jj u_x u_y u pressure obstacle`, jj outer / ii inner (SerialCode:679-724);
@@ -130,7 +302,7 @@ static int* read_obstacles(const char* path, const lbm_param_t* p)
  * formatted by all host cores (snprintf into per-band buffers) and written in order. */
 typedef struct {
     const lbm_param_t* p;
-    const int* obstacles;
+    const uint32_t* obstacles; /* packed, see read_obstacles */
     const float *ux, *uy, *u, *pressure;
     int row0, row1;
     char* buf;
@@ -142,6 +314,7 @@ static void* format_rows(void* arg)
 {
     format_job* j = (format_job*)arg;
     const int nx = j->p->nx;
+    const size_t wpr = ((size_t)nx + 31) / 32;
     const size_t cap = (size_t)(j->row1 - j->row0) * (size_t)nx * 112 + 16; /* a line is at most 2*11+4*20+1+7 bytes */
     j->buf = malloc(cap);
     if (!j->buf) {
@@ -153,13 +326,13 @@ static void* format_rows(void* arg)
         for (int ii = 0; ii < nx; ii++) {
             const size_t c = (size_t)ii + (size_t)jj * nx;
             at += (size_t)snprintf(j->buf + at, cap - at, "%d %d %.12E %.12E %.12E %.12E %d\n", ii, jj, j->ux[c], j->uy[c], j->u[c],
-                                   j->pressure[c], j->obstacles[c]);
+                                   j->pressure[c], obstacle_at(j->obstacles, wpr, ii, jj));
         }
     j->len = at;
     return NULL;
 }
 
-static void write_final_state(const lbm_param_t* p, const int* obstacles, const float* ux, const float* uy, const float* u,
+static void write_final_state(const lbm_param_t* p, const uint32_t* obstacles, const float* ux, const float* uy, const float* u,
                               const float* pressure)
 {
     FILE* fp = fopen(FINAL_STATE_FILE, "w");
@@ -240,7 +413,21 @@ int main(int argc, char* argv[])
     lbm_param_t params;
     read_params(paramfile, &params);
     if (params.nx < 1 || params.ny < 2 || params.maxIters < 0) DIE("grid size / iteration count out of range");
-    int* obstacles = read_obstacles(obstaclefile, &params);
+    const double parse_tic = wall_seconds();
+    uint32_t* obstacles = read_obstacles(obstaclefile, &params); /* 1 bit per cell */
+    const double parse_toc = wall_seconds();
+    if (env_int("LBM_PARSE_ONLY", 0)) {
+        const size_t nw = (((size_t)params.nx + 31) / 32) * (size_t)params.ny;
+        unsigned long long blocked = 0, h = 1469598103934665603ULL;
+        for (size_t i = 0; i < nw; i++) {
+            blocked += (unsigned long long)__builtin_popcount(obstacles[i]);
+            for (int b = 0; b < 4; b++) h = (h ^ ((obstacles[i] >> (8 * b)) & 0xffu)) * 1099511628211ULL;
+        }
+        printf("parsed: nx=%d ny=%d maxIters=%d blocked=%llu fnv1a=%016llx obstacle_parse_seconds=%.6f\n", params.nx, params.ny,
+               params.maxIters, blocked, h, parse_toc - parse_tic);
+        free(obstacles);
+        return EXIT_SUCCESS;
+    }
 
     lbm_options_t opt;
     lbm_default_options(&opt);
@@ -255,7 +442,7 @@ int main(int argc, char* argv[])
     const int skip_final = env_int("LBM_SKIP_FINAL_STATE", 0);
 
     lbm_lattice_t* lat = NULL;
-    LBM_CALL(lbm_create(&params, obstacles, ngpus, &opt, &lat));
+    LBM_CALL(lbm_create_packed(&params, obstacles, ngpus, &opt, &lat));
     float* av_vels = malloc(sizeof(float) * (size_t)(params.maxIters > 0 ? params.maxIters : 1));
     if (!av_vels) DIE("cannot allocate memory for av_vels");
     LBM_CALL(lbm_sync(lat));

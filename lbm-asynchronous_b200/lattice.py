@@ -37,6 +37,27 @@ def _options(arith, halo_mode, halo_lag, use_graph, kernel, block) -> Options:
     return o
 
 
+def pack_obstacles(obstacles: np.ndarray) -> np.ndarray:
+    """int map [rows, nx] (non-zero = blocked) -> the packed map lbm_create_packed takes: uint32[rows, ceil(nx/32)],
+    cell x is bit x % 32 of word x // 32."""
+    ob = np.asarray(obstacles) != 0
+    rows, nx = ob.shape
+    words = (nx + 31) // 32
+    padded = np.zeros((rows, words * 32), dtype=np.uint8)
+    padded[:, :nx] = ob
+    return np.packbits(padded, axis=1, bitorder="little").view("<u4").reshape(rows, words).copy()
+
+
+def _is_packed(obstacles, nx: int) -> bool:
+    a = np.asarray(obstacles)
+    return a.dtype == np.uint32 and a.ndim == 2 and a.shape[1] == (nx + 31) // 32 and not (nx == a.shape[1])
+
+
+def _uptr(a: np.ndarray):
+    assert a.dtype == np.uint32 and a.flags.c_contiguous
+    return a.ctypes.data_as(C.POINTER(C.c_uint))
+
+
 def make_param(nx, ny, maxIters=0, reynolds_dim=10, density=0.1, accel=0.005, omega=1.85) -> Param:
     return Param(int(nx), int(ny), int(maxIters), int(reynolds_dim), float(density), float(accel), float(omega))
 
@@ -54,11 +75,17 @@ class Lattice:
                  halo_mode="sync", halo_lag=0, use_graph=True, kernel=0, block=0):
         self.param = param
         self.nx, self.ny = param.nx, param.ny
-        ob = np.ascontiguousarray(obstacles, dtype=np.int32).reshape(param.ny, param.nx)
         opt = _options(arith, halo_mode, halo_lag, use_graph, kernel, block)
         self._h = C.c_void_p()
         self._rows = param.ny
         self._last_iters = 0
+        if _is_packed(obstacles, param.nx):  # uint32[ny, ceil(nx/32)]: one bit per cell (pack_obstacles)
+            if devices is not None:
+                raise ValueError("a packed obstacle map goes through lbm_create_packed (devices 0..ngpus-1)")
+            pk = np.ascontiguousarray(obstacles, dtype=np.uint32)
+            check(library().lbm_create_packed(C.byref(param), _uptr(pk), int(ngpus), C.byref(opt), C.byref(self._h)))
+            return
+        ob = np.ascontiguousarray(obstacles, dtype=np.int32).reshape(param.ny, param.nx)
         if devices is not None:
             dev = (C.c_int * len(devices))(*devices)
             check(library().lbm_create_on(C.byref(param), _iptr(ob), len(devices), dev, C.byref(opt), C.byref(self._h)))
@@ -195,10 +222,15 @@ class SlabLattice(Lattice):
         self.nx, self.ny = param.nx, param.ny
         self.row0, self.row1, self.rank, self.nranks = int(row0), int(row1), int(rank), int(nranks)
         self._rows = self.row1 - self.row0
-        ob = np.ascontiguousarray(obstacle_rows, dtype=np.int32).reshape(self._rows, param.nx)
         opt = _options(arith, halo_mode, halo_lag, use_graph, kernel, block)
         self._h = C.c_void_p()
         self._last_iters = 0
+        if _is_packed(obstacle_rows, param.nx):
+            pk = np.ascontiguousarray(obstacle_rows, dtype=np.uint32)
+            check(library().lbm_create_slab_packed(C.byref(param), _uptr(pk), self.row0, self.row1, self.rank, self.nranks,
+                                                   int(device), C.byref(opt), C.byref(self._h)))
+            return
+        ob = np.ascontiguousarray(obstacle_rows, dtype=np.int32).reshape(self._rows, param.nx)
         check(library().lbm_create_slab(C.byref(param), _iptr(ob), self.row0, self.row1, self.rank, self.nranks,
                                         int(device), C.byref(opt), C.byref(self._h)))
 
@@ -213,4 +245,4 @@ class SlabLattice(Lattice):
         check(library().lbm_halo_connect(self._h, s, n))
 
 
-__all__ = ["Lattice", "SlabLattice", "LbmError", "make_param", "av_from_sums"]
+__all__ = ["Lattice", "SlabLattice", "LbmError", "make_param", "av_from_sums", "pack_obstacles"]

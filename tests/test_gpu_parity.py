@@ -471,3 +471,31 @@ def test_large_grid_with_partial_tiles_bit_exact(gpu, pkg, orc):
     assert_lattice_equal(cells, ref_cells, obst)
     tot, n = orc.tot_u_f64(p, ref_cells, obst)
     assert av[-1] == pytest.approx(tot / n, rel=2e-6)
+
+
+def test_packed_obstacle_map_gives_the_same_lattice(gpu, pkg, orc):
+    """lbm_create_packed / lbm_create_slab_packed (one bit per cell, the device's own layout) == lbm_create from
+    the reference's int map, including widths that are not a multiple of 32 and stray bits beyond nx."""
+    for nx, ny in ((100, 40), (128, 33), (37, 19)):
+        p, obst, cells0 = random_case(orc, nx, ny, seed=nx)
+        packed = pkg.pack_obstacles(obst)
+        assert packed.shape == (ny, (nx + 31) // 32) and packed.dtype == np.uint32
+        if nx % 32:
+            packed[:, -1] |= np.uint32(0xFFFFFFFF) << np.uint32(nx % 32)  # garbage beyond nx must be ignored
+        outs = []
+        for ob in (obst, packed):
+            with pkg.Lattice(to_param(p), ob) as lat:
+                assert lat.fluid_cells == int((obst == 0).sum())
+                lat.upload(cells0)
+                lat.run(9)
+                outs.append(lat.cells())
+        assert np.array_equal(bits(outs[0]), bits(outs[1]))
+    p, obst, cells0 = random_case(orc, 128, 24, seed=3, walls=False)
+    ref_cells, _ = orc.run(p, obst, 9, cells=cells0)
+    lat = pkg.SlabLattice(to_param(p), pkg.pack_obstacles(obst), 0, p.ny, 0, 1, 0)
+    h = lat.export_handle()
+    lat.connect(h, h)
+    lat.upload(cells0)
+    lat.run(9)
+    assert_lattice_equal(lat.cells(), ref_cells, obst)
+    lat.close()
