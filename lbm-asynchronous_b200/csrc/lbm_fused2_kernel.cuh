@@ -78,6 +78,188 @@ __device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, f
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// ---- the collision of four cells as ONE basic block ----------------------------------------------------------
+// update_cell() guards each of its special sequences (division by rho, the constant divisions, the square root)
+// with its own test and branch to an IEEE slow path: four branches per cell, sixteen per thread and row.  ptxas
+// schedules within basic blocks, so those branches keep it from interleaving the four cells' dependency chains --
+// on this kernel, which is bound by instruction issue, "wait" (fixed-latency dependency) was the top stall.  Here
+// the sequences run unguarded for all four cells, two cheap window tests per cell decide afterwards whether every
+// one of them was inside the window its sequence is exact in, and a thread that ever fails (it never does in a
+// physical flow) simply redoes its four cells with update_cell()'s guarded code.  Windows:
+//   early: 2^-20 <= rho <= 2^20 and max(|m_x|, |m_y|) <= 2 rho  (so |u| <~ 2)
+//          => div2 sequence exact (rho in [2^-40, 2^40], |m| < 2^40, lbm_kernels.cuh), the constant divisions exact
+//             (|u| < 2^58), and everything after them is plain IEEE arithmetic: the new populations are exact;
+//   late:  the same test on the moments of the NEW populations (4 rho' as the momentum bound)
+//          => div2 exact again, u'^2 <= 2^100, so speed_from_sq's sequence is exact where u'^2 >= 2^-100 and the
+//             result is 0 below (a select, as in speed_from_sq).
+// NaN operands fail both tests.  The fast flavour uses the same structure around its own arithmetic.
+__device__ __forceinline__ void div2_unguarded(float a1, float a2, float b, float& q1, float& q2)
+{
+    float y0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(b));
+    const float e = __fmaf_rn(-b, y0, 1.f);
+    const float y = __fmaf_rn(y0, e, y0);
+    const float p1 = __fmul_rn(a1, y), p2 = __fmul_rn(a2, y);
+    q1 = __fmaf_rn(y, __fmaf_rn(-b, p1, a1), p1);
+    q2 = __fmaf_rn(y, __fmaf_rn(-b, p2, a2), p2);
+}
+__device__ __forceinline__ float speed_from_sq_select(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    const float g = __fmul_rn(x, y), h = __fmul_rn(y, 0.5f);
+    const float s = __fmaf_rn(__fmaf_rn(-g, g, x), h, g);
+    return x >= 7.888609052210118e-31f /* 2^-100 */ ? s : 0.f;
+}
+__device__ __forceinline__ bool in_window(float rho, float mx, float my, float lo, float hi, float bound)
+{
+    return rho >= lo && rho <= hi && fmaxf(fabsf(mx), fabsf(my)) <= __fmul_rn(bound, rho);
+}
+
+template <bool STRICT>
+__device__ __forceinline__ bool collide4_straight(const float (&t)[Q][4], float omega, float (&c)[Q][4], float (&speed)[4])
+{
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if constexpr (STRICT) {
+            // SerialCode/d2q9-bgk.c:325-401 in the reference's operation order (see update_cell for the identities)
+            float rho = __fadd_rn(0.f, t[0][j]);
+#pragma unroll
+            for (int k = 1; k < Q; k++) rho = __fadd_rn(rho, t[k][j]);
+            const float mx = __fsub_rn(__fadd_rn(__fadd_rn(t[1][j], t[5][j]), t[8][j]), __fadd_rn(__fadd_rn(t[3][j], t[6][j]), t[7][j]));
+            const float my = __fsub_rn(__fadd_rn(__fadd_rn(t[2][j], t[5][j]), t[6][j]), __fadd_rn(__fadd_rn(t[4][j], t[7][j]), t[8][j]));
+            ok = ok && in_window(rho, mx, my, 9.5367431640625e-07f /* 2^-20 */, 1048576.f /* 2^20 */, 2.f);
+            float ux, uy;
+            div2_unguarded(mx, my, rho, ux, uy);
+            const float uxx = __fmul_rn(ux, ux), uyy = __fmul_rn(uy, uy);
+            const float u_sq = __fadd_rn(uxx, uyy);
+            const float u5 = __fadd_rn(ux, uy), u6 = __fsub_rn(uy, ux);
+            const float v = div_const(u_sq, LBM_2CSQ, LBM_R_2CSQ);
+            const float q1 = div_const(ux, LBM_C_SQ, LBM_R_C_SQ), q2 = div_const(uy, LBM_C_SQ, LBM_R_C_SQ);
+            const float q5 = div_const(u5, LBM_C_SQ, LBM_R_C_SQ), q6 = div_const(u6, LBM_C_SQ, LBM_R_C_SQ);
+            const float s1 = div_const(uxx, LBM_2CSQ2, LBM_R_2CSQ2), s2 = div_const(uyy, LBM_2CSQ2, LBM_R_2CSQ2);
+            const float s5 = div_const(__fmul_rn(u5, u5), LBM_2CSQ2, LBM_R_2CSQ2), s6 = div_const(__fmul_rn(u6, u6), LBM_2CSQ2, LBM_R_2CSQ2);
+            const float w0r = __fmul_rn(LBM_W0, rho), w1r = __fmul_rn(LBM_W1, rho), w2r = __fmul_rn(LBM_W2, rho);
+            float d[Q];
+            d[0] = __fmul_rn(w0r, __fsub_rn(1.f, v));
+            d[1] = __fmul_rn(w1r, __fsub_rn(__fadd_rn(__fadd_rn(1.f, q1), s1), v));
+            d[3] = __fmul_rn(w1r, __fsub_rn(__fadd_rn(__fsub_rn(1.f, q1), s1), v));
+            d[2] = __fmul_rn(w1r, __fsub_rn(__fadd_rn(__fadd_rn(1.f, q2), s2), v));
+            d[4] = __fmul_rn(w1r, __fsub_rn(__fadd_rn(__fsub_rn(1.f, q2), s2), v));
+            d[5] = __fmul_rn(w2r, __fsub_rn(__fadd_rn(__fadd_rn(1.f, q5), s5), v));
+            d[7] = __fmul_rn(w2r, __fsub_rn(__fadd_rn(__fsub_rn(1.f, q5), s5), v));
+            d[6] = __fmul_rn(w2r, __fsub_rn(__fadd_rn(__fadd_rn(1.f, q6), s6), v));
+            d[8] = __fmul_rn(w2r, __fsub_rn(__fadd_rn(__fsub_rn(1.f, q6), s6), v));
+#pragma unroll
+            for (int k = 0; k < Q; k++) c[k][j] = __fadd_rn(t[k][j], __fmul_rn(omega, __fsub_rn(d[k], t[k][j])));
+            // |u| of the stored values, SerialCode:425-452
+            float r2 = __fadd_rn(0.f, c[0][j]);
+#pragma unroll
+            for (int k = 1; k < Q; k++) r2 = __fadd_rn(r2, c[k][j]);
+            const float nx_ = __fsub_rn(__fadd_rn(__fadd_rn(c[1][j], c[5][j]), c[8][j]), __fadd_rn(__fadd_rn(c[3][j], c[6][j]), c[7][j]));
+            const float ny_ = __fsub_rn(__fadd_rn(__fadd_rn(c[2][j], c[5][j]), c[6][j]), __fadd_rn(__fadd_rn(c[4][j], c[7][j]), c[8][j]));
+            ok = ok && in_window(r2, nx_, ny_, 4.76837158203125e-07f /* 2^-21 */, 2097152.f /* 2^21 */, 4.f);
+            float vx, vy;
+            div2_unguarded(nx_, ny_, r2, vx, vy);
+            speed[j] = speed_from_sq_select(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
+        } else {
+            float rho = t[0][j];
+#pragma unroll
+            for (int k = 1; k < Q; k++) rho += t[k][j];
+            const float mx = (t[1][j] + t[5][j] + t[8][j]) - (t[3][j] + t[6][j] + t[7][j]);
+            const float my = (t[2][j] + t[5][j] + t[6][j]) - (t[4][j] + t[7][j] + t[8][j]);
+            ok = ok && in_window(rho, mx, my, 9.5367431640625e-07f, 1048576.f, 2.f);
+            float ux, uy;
+            div2_unguarded(mx, my, rho, ux, uy);
+            const float u_sq = fmaf(ux, ux, uy * uy);
+            const float base = fmaf(-LBM_R_2CSQ, u_sq, 1.f);
+            const float u5 = ux + uy, u6 = uy - ux;
+            const float e1 = fmaf(LBM_R_2CSQ2 * ux, ux, base);
+            const float e2 = fmaf(LBM_R_2CSQ2 * uy, uy, base);
+            const float e5 = fmaf(LBM_R_2CSQ2 * u5, u5, base);
+            const float e6 = fmaf(LBM_R_2CSQ2 * u6, u6, base);
+            const float w0r = LBM_W0 * rho, w1r = LBM_W1 * rho, w2r = LBM_W2 * rho;
+            float d[Q];
+            d[0] = w0r * base;
+            d[1] = w1r * fmaf(LBM_R_C_SQ, ux, e1);
+            d[3] = w1r * fmaf(-LBM_R_C_SQ, ux, e1);
+            d[2] = w1r * fmaf(LBM_R_C_SQ, uy, e2);
+            d[4] = w1r * fmaf(-LBM_R_C_SQ, uy, e2);
+            d[5] = w2r * fmaf(LBM_R_C_SQ, u5, e5);
+            d[7] = w2r * fmaf(-LBM_R_C_SQ, u5, e5);
+            d[6] = w2r * fmaf(LBM_R_C_SQ, u6, e6);
+            d[8] = w2r * fmaf(-LBM_R_C_SQ, u6, e6);
+#pragma unroll
+            for (int k = 0; k < Q; k++) c[k][j] = fmaf(omega, d[k] - t[k][j], t[k][j]);
+            float r2 = c[0][j];
+#pragma unroll
+            for (int k = 1; k < Q; k++) r2 += c[k][j];
+            const float nx_ = (c[1][j] + c[5][j] + c[8][j]) - (c[3][j] + c[6][j] + c[7][j]);
+            const float ny_ = (c[2][j] + c[5][j] + c[6][j]) - (c[4][j] + c[7][j] + c[8][j]);
+            ok = ok && in_window(r2, nx_, ny_, 4.76837158203125e-07f, 2097152.f, 4.f);
+            speed[j] = __fdividef(speed_from_sq_select(fmaf(nx_, nx_, ny_ * ny_)), r2);
+        }
+    }
+    return ok;
+}
+
+// update4() for this kernel: collide4_straight, the bounce-back selects only when some lane of the warp holds an
+// obstacle (most warps: 0.5 % of the benchmark's cells are blocked), and the |u| of the four cells straight into
+// one 64-bit total (any split into the two words the host adds up is equivalent)
+template <bool STRICT>
+__device__ __forceinline__ void update4_total(const float (&t)[Q][4], uint32_t obits, bool counted, bool accel, float omega, float w1a,
+                                              float w2a, float (&o)[Q][4], unsigned long long& total, unsigned& nbad)
+{
+    float speed[4];
+    if (!collide4_straight<STRICT>(t, omega, o, speed)) {
+        // some operand left the windows the unguarded sequences are exact in: the guarded code, all four cells
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float tj[Q], oc[Q];
+#pragma unroll
+            for (int k = 0; k < Q; k++) tj[k] = t[k][j];
+            speed[j] = collide_cell<STRICT>(tj, omega, oc);
+#pragma unroll
+            for (int k = 0; k < Q; k++) o[k][j] = oc[k];
+        }
+    }
+    if (__any_sync(0xffffffffu, obits != 0u)) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool solid = (obits >> j) & 1u;
+            // bounce-back permutation, SerialCode/d2q9-bgk.c:287-299 (speed 0 keeps the streamed value)
+            o[0][j] = solid ? t[0][j] : o[0][j];
+            o[1][j] = solid ? t[3][j] : o[1][j];
+            o[2][j] = solid ? t[4][j] : o[2][j];
+            o[3][j] = solid ? t[1][j] : o[3][j];
+            o[4][j] = solid ? t[2][j] : o[4][j];
+            o[5][j] = solid ? t[7][j] : o[5][j];
+            o[6][j] = solid ? t[8][j] : o[6][j];
+            o[7][j] = solid ? t[5][j] : o[7][j];
+            o[8][j] = solid ? t[6][j] : o[8][j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const bool cnt = counted && !((obits >> j) & 1u);
+        const bool bad = !(speed[j] < FIX_LIMIT);
+        total += (bad || !cnt) ? 0ull : __float2ull_rn(speed[j] * FIX_SCALE);
+        nbad += (bad && cnt) ? 1u : 0u;
+    }
+    if (accel) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float oc[Q];
+#pragma unroll
+            for (int k = 0; k < Q; k++) oc[k] = o[k][j];
+            accelerate_cell(oc, (obits >> j) & 1u, w1a, w2a);
+#pragma unroll
+            for (int k = 0; k < Q; k++) o[k][j] = oc[k];
+        }
+    }
+}
+
 // source row of plane K for lattice row g of a boundary unit: a lattice row, the periodic wrap of a single
 // slab, or an entry of the halo ring the neighbouring GPU filled (near row: planes 0,1,3 -> entries 0..2, the
 // three planes crossing towards this slab -> 3..5; far row: the crossing planes -> 6..8)
@@ -356,17 +538,30 @@ __global__ void __launch_bounds__(32 * R, MINB)
                         if (pe0) t[3][0] = pa[0], t[6][0] = pa[1], t[7][0] = pa[2], t[0][0] = pb[0], t[2][0] = pb[1], t[4][0] = pb[2];
                         if (pe1) t[3][3] = pa[0], t[6][3] = pa[1], t[7][3] = pa[2];
                     }
+                    if (phase == 0 && (west || east)) {
+                        // columns the copy engine zero-filled and nobody will read (x < -1, x > nx): give them a fluid at
+                        // rest, or their 0 / 0 would drag the whole warp through the IEEE slow paths on every row
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int x = xg + j;
+                            if (x < -1 || x > a.nx) {
+                                t[0][j] = 0.04f;
+#pragma unroll
+                                for (int k = 1; k < Q; k++) t[k][j] = k < 5 ? 0.01f : 0.0025f;
+                            }
+                        }
+                    }
                     const uint32_t obits = (oword >> (xo & 31)) & 0xfu;
                     // cells whose |u| this unit owns: its core columns, and in phase 0 its own rows only
                     const bool counted = phase ? (lane < 30 && xg < a.nx)
                                                : (y >= ya && y < yb && lane >= 1 && lane <= 30 && xg < a.nx);
                     const bool accel = (a.accel_row >= 0) && (y == a.accel_row) && (phase == 0 || live2);
                     float o[Q][4];
-                    SpeedAcc acc = {0u, 0u, 0u};
-                    update4<STRICT>(t, obits, counted, accel, a.omega, a.w1a, a.w2a, o, acc);
-                    const unsigned long long tot = static_cast<unsigned long long>(acc.lo) + (static_cast<unsigned long long>(acc.hi) << FIX_SPLIT);
-                    if (phase) acc_b += tot, bad_b += acc.bad;
-                    else acc_a += tot, bad_a += acc.bad;
+                    unsigned long long tot = 0ull;
+                    unsigned nbad = 0u;
+                    update4_total<STRICT>(t, obits, counted, accel, a.omega, a.w1a, a.w2a, o, tot, nbad);
+                    if (phase) acc_b += tot, bad_b += nbad;
+                    else acc_a += tot, bad_a += nbad;
 
                     if (phase == 0) {
                         const uint32_t dst = buf2_s + ((q % RB) * F2_B2ROW + 4 * lane) * 4;
