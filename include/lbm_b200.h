@@ -184,6 +184,13 @@ long long lbm_kernel_launches(const lbm_lattice_t* lat);
  * operand sets drawn from the operand window they are specified for; mismatches[0] counts
  * differing quotients, mismatches[1] differing roots.  Both must be 0. */
 int lbm_selftest(int device, unsigned long long pairs, unsigned long long seed, unsigned long long* mismatches /* [2] */);
+/* Device self-test of the four-cell collision the step kernels run (packed fp32 instructions, one basic block,
+ * lbm_collide4.cuh) against the scalar per-cell code with its guarded IEEE paths, on about `sets` pseudo-random
+ * groups of four cells (lattice-like, rough and arbitrary populations, random obstacle bits): mismatches[0] counts
+ * differing population words, mismatches[1] differing |u| words.  Both must be 0 for arith = LBM_ARITH_STRICT (the
+ * packed code is the reference's operation sequence, SerialCode/d2q9-bgk.c:325-401,425-452, two cells per
+ * instruction); the fast flavour may differ from its scalar form by contraction only. */
+int lbm_selftest_collide(int device, int arith, unsigned long long sets, unsigned long long seed, unsigned long long* mismatches /* [2] */);
 /* rows [row0,row1) and device of slab `i` (i < lbm_num_slabs) */
 int lbm_num_slabs(const lbm_lattice_t* lat);
 int lbm_slab_info(const lbm_lattice_t* lat, int i, int* row0, int* row1, int* device);

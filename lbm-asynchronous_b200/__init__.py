@@ -22,6 +22,7 @@ from .capi import (  # noqa: F401
     library_path,
     partition,
     selftest,
+    selftest_collide,
 )
 from .lattice import Lattice, SlabLattice, av_from_sums, pack_obstacles  # noqa: F401
 from .inputs import check_metric, read_obstacles, read_params  # noqa: F401

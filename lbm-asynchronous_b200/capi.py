@@ -21,7 +21,7 @@ SYMBOLS = (
     "lbm_create_packed", "lbm_packed_words_per_row", "lbm_create_slab", "lbm_create_slab_packed", "lbm_halo_export", "lbm_halo_connect", "lbm_set_stream", "lbm_run", "lbm_sync", "lbm_av_vels",
     "lbm_tot_u_sums", "lbm_av_from_sums", "lbm_fluid_cells", "lbm_steps_done", "lbm_av_velocity", "lbm_total_density",
     "lbm_final_state", "lbm_download_cells", "lbm_upload_cells", "lbm_last_run_ms", "lbm_kernel_launches",
-    "lbm_num_slabs", "lbm_slab_info", "lbm_destroy", "lbm_selftest",
+    "lbm_num_slabs", "lbm_slab_info", "lbm_destroy", "lbm_selftest", "lbm_selftest_collide",
 )
 
 
@@ -110,6 +110,7 @@ def library() -> C.CDLL:
         "lbm_slab_info": (C.c_int, [vp, C.c_int, ip, ip, ip]),
         "lbm_destroy": (None, [vp]),
         "lbm_selftest": (C.c_int, [C.c_int, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]),
+        "lbm_selftest_collide": (C.c_int, [C.c_int, C.c_int, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -129,6 +130,14 @@ def selftest(pairs: int = 1 << 30, seed: int = 1, device: int = 0):
     """lbm_selftest: (differing quotients, differing roots) over ~`pairs` random operand sets; both must be 0."""
     out = (C.c_ulonglong * 2)()
     check(library().lbm_selftest(device, pairs, seed, out))
+    return int(out[0]), int(out[1])
+
+
+def selftest_collide(arith: str = "strict", sets: int = 1 << 24, seed: int = 1, device: int = 0):
+    """lbm_selftest_collide: (differing population words, differing |u| words) of the packed four-cell collision
+    against the scalar per-cell code over ~`sets` random groups of four cells."""
+    out = (C.c_ulonglong * 2)()
+    check(library().lbm_selftest_collide(device, {"strict": 0, "fast": 1}[arith], sets, seed, out))
     return int(out[0]), int(out[1])
 
 

@@ -224,23 +224,20 @@ bool tma_by_shape(int ty, int stages, int minb, TmaChoice* c)
 typedef void (*f2_fn)(CUtensorMap, CUtensorMap, Fused2Args);
 struct F2Choice {
     int r, srows, stages, minb;
-    bool flags;
     f2_fn fn;
 };
 template <bool STRICT>
-bool f2_by_shape(int r, int srows, int stages, int minb, bool flags, F2Choice* c)
+bool f2_by_shape(int r, int srows, int stages, int minb, F2Choice* c)
 {
-#define LBM_F2_CASE(R_, S_, N_, M_, F_)                                           \
-    if (r == R_ && srows == S_ && stages == N_ && minb == M_ && flags == F_) {    \
-        *c = {R_, S_, N_, M_, F_, step2_kernel<STRICT, R_, S_, N_, M_, F_>};      \
-        return true;                                                              \
+#define LBM_F2_CASE(R_, S_, N_, M_)                                      \
+    if (r == R_ && srows == S_ && stages == N_ && minb == M_) {          \
+        *c = {R_, S_, N_, M_, step2_kernel<STRICT, R_, S_, N_, M_>};     \
+        return true;                                                     \
     }
-    LBM_F2_CASE(8, 4, 3, 2, false)
-    LBM_F2_CASE(8, 4, 3, 2, true)
-    LBM_F2_CASE(16, 8, 3, 1, false)
-    LBM_F2_CASE(16, 8, 3, 1, true)
-    LBM_F2_CASE(16, 4, 6, 1, true)
-    LBM_F2_CASE(8, 8, 2, 1, true)
+    LBM_F2_CASE(8, 4, 3, 2)
+    LBM_F2_CASE(16, 8, 3, 1)
+    LBM_F2_CASE(16, 4, 6, 1)
+    LBM_F2_CASE(12, 4, 4, 1)
 #undef LBM_F2_CASE
     return false;
 }
@@ -252,8 +249,7 @@ bool f2_by_shape(int r, int srows, int stages, int minb, bool flags, F2Choice* c
 //                stages, 1 CTA/SM) for the interior rows when nx % 4 == 0, nx >= 128 and the slab has >= 3 rows,
 //                step_vec4_kernel / step_scalar_kernel for the rest
 //   2RRSNM       step2_kernel with RR warps (rows per iteration), S rows per stage, N stages, M CTAs per SM asked of
-//                the compiler; M + 4 = the same with flag-based instead of barrier-based synchronisation
-//                (208432 208436 216831 216835 216465 208825)
+//                the compiler (208432 216831 216461 212441)
 //   1TTSM        step_tma_kernel with TT rows per tile, S stages, M resident CTAs per SM asked of the compiler
 //                (10823 10822 10832 10831 10841 10434 10444 10443 10462 11621 11631)
 //   H M (10..39) step_vec4_kernel for every row: hint = H-1 (0 plain, 1 ld.nc.no_allocate, 2 + st.cs), min blocks M
@@ -270,7 +266,7 @@ struct KernelChoice {
     int hint, block, minb;
     bool tma;
     int tma_ty, tma_stages, tma_minb;
-    bool f2, f2_flags;
+    bool f2;
     int f2_r, f2_srows, f2_stages, f2_minb;
 };
 KernelChoice choose_kernel(const lbm_options_t& o, int nx)
@@ -292,13 +288,12 @@ KernelChoice choose_kernel(const lbm_options_t& o, int nx)
     // pairs of steps: default wherever the TMA path applies; an explicit single-step variant (1TTSM, H M, 99)
     // or a deterministic halo lag (defined per single step) switches it off
     k.f2 = k.tma && (o.kernel == 0 || (o.kernel >= 200 && o.kernel <= 204) || o.kernel >= 200000) && o.halo_lag == 0;
-    k.f2_r = 8, k.f2_srows = 4, k.f2_stages = 3, k.f2_minb = 2, k.f2_flags = false;
+    k.f2_r = 8, k.f2_srows = 4, k.f2_stages = 3, k.f2_minb = 2;
     if (o.kernel >= 200000) {
         k.f2_r = (o.kernel - 200000) / 1000;
         k.f2_srows = (o.kernel / 100) % 10;
         k.f2_stages = (o.kernel / 10) % 10;
         k.f2_minb = o.kernel % 10;
-        if (k.f2_minb > 4) k.f2_minb -= 4, k.f2_flags = true;
     } else if (o.kernel >= 10000) {
         k.tma_ty = (o.kernel - 10000) / 100;
         k.tma_stages = (o.kernel / 10) % 10;
@@ -981,8 +976,8 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
     }
     if (k.f2 && L->tma_kernel) {
         F2Choice c;
-        const bool ok = strict ? f2_by_shape<true>(k.f2_r, k.f2_srows, k.f2_stages, k.f2_minb, k.f2_flags, &c)
-                               : f2_by_shape<false>(k.f2_r, k.f2_srows, k.f2_stages, k.f2_minb, k.f2_flags, &c);
+        const bool ok = strict ? f2_by_shape<true>(k.f2_r, k.f2_srows, k.f2_stages, k.f2_minb, &c)
+                               : f2_by_shape<false>(k.f2_r, k.f2_srows, k.f2_stages, k.f2_minb, &c);
         if (!ok)
             return fail(LBM_EINVAL, "no step2_kernel variant with %d consumer warps, %d rows per stage, %d stages, %d CTAs per SM", k.f2_r,
                         k.f2_srows, k.f2_stages, k.f2_minb);
@@ -1905,6 +1900,27 @@ int lbm_selftest(int device, unsigned long long pairs, unsigned long long seed, 
     if (e == cudaSuccess) e = cudaMemcpy(mismatches, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return fail(LBM_ECUDA, "self-test kernel failed: %s", cudaGetErrorString(e));
+    return LBM_OK;
+}
+
+int lbm_selftest_collide(int device, int arith, unsigned long long sets, unsigned long long seed, unsigned long long* mismatches)
+{
+    if (!mismatches) return fail(LBM_EINVAL, "NULL argument");
+    if (arith != LBM_ARITH_STRICT && arith != LBM_ARITH_FAST) return fail(LBM_EINVAL, "unknown arithmetic flavour %d", arith);
+    int rc = check_device_available();
+    if (rc) return rc;
+    CU(cudaSetDevice(device));
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    CU(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+    const unsigned blocks = 148 * 4, threads = 128;
+    const unsigned long long per_thread = (sets + static_cast<unsigned long long>(blocks) * threads - 1) / (static_cast<unsigned long long>(blocks) * threads);
+    if (arith == LBM_ARITH_STRICT) selftest_collide_kernel<true><<<blocks, threads>>>(per_thread, seed, 1.85f, d);
+    else selftest_collide_kernel<false><<<blocks, threads>>>(per_thread, seed, 1.85f, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(mismatches, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(LBM_ECUDA, "collision self-test kernel failed: %s", cudaGetErrorString(e));
     return LBM_OK;
 }
 

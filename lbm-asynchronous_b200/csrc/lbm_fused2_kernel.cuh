@@ -35,12 +35,6 @@
 
 namespace lbm {
 
-#ifndef LBM_F2_INTERLEAVE
-#define LBM_F2_INTERLEAVE 1 // cells whose collisions are written side by side (1, 2 or 4)
-#endif
-#ifndef LBM_F2_EXP_CELLS
-#define LBM_F2_EXP_CELLS 4 // diagnostics only: < 4 skips the collision of the remaining cells of every lane (wrong results)
-#endif
 constexpr int F2_CORE = 120;          // columns of a strip that a unit finally writes (30 lanes x 4 cells)
 constexpr int F2_W1 = 128;            // columns of a strip computed for the intermediate step
 constexpr int F2_B2ROW = Q * F2_W1;   // floats per ring row of intermediate results: [plane][128]
@@ -82,258 +76,6 @@ __device__ __forceinline__ float lds1(uint32_t addr)
 __device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, float d)
 {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-// ---- the collision of four cells as ONE basic block ----------------------------------------------------------
-// update_cell() guards each of its special sequences (division by rho, the constant divisions, the square root)
-// with its own test and branch to an IEEE slow path: four branches per cell, sixteen per thread and row.  ptxas
-// schedules within basic blocks, so those branches keep it from interleaving the four cells' dependency chains --
-// on this kernel, which is bound by instruction issue, "wait" (fixed-latency dependency) was the top stall.  Here
-// the moments of the four cells are formed first and tested against an "early" window; a thread with a cell outside
-// it (never in a physical flow) takes update_cell()'s guarded code for its four cells; everybody else runs the
-// sequences unguarded in one block, and a "late" window test on the new populations decides whether the |u| of a
-// cell has to be redone with the guarded code (the new populations themselves are exact by then).  Windows:
-//   early: 2^-20 <= rho <= 2^20 and max(|m_x|, |m_y|) <= 2 rho  (so |u| <~ 2)
-//          => div2 sequence exact (rho in [2^-40, 2^40], |m| < 2^40, lbm_kernels.cuh), the constant divisions exact
-//             (|u| < 2^58), and everything after them is plain IEEE arithmetic: the new populations are exact;
-//   late:  the same test on the moments of the NEW populations (4 rho' as the momentum bound)
-//          => div2 exact again, u'^2 <= 2^100, so speed_from_sq's sequence is exact where u'^2 >= 2^-100 and the
-//             result is 0 below (a select, as in speed_from_sq).
-// NaN operands fail both tests.  The fast flavour uses the same structure around its own arithmetic.
-__device__ __forceinline__ void div2_unguarded(float a1, float a2, float b, float& q1, float& q2)
-{
-    float y0;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(b));
-    const float e = __fmaf_rn(-b, y0, 1.f);
-    const float y = __fmaf_rn(y0, e, y0);
-    const float p1 = __fmul_rn(a1, y), p2 = __fmul_rn(a2, y);
-    q1 = __fmaf_rn(y, __fmaf_rn(-b, p1, a1), p1);
-    q2 = __fmaf_rn(y, __fmaf_rn(-b, p2, a2), p2);
-}
-__device__ __forceinline__ float speed_from_sq_select(float x)
-{
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    const float g = __fmul_rn(x, y), h = __fmul_rn(y, 0.5f);
-    const float s = __fmaf_rn(__fmaf_rn(-g, g, x), h, g);
-    return x >= 7.888609052210118e-31f /* 2^-100 */ ? s : 0.f;
-}
-__device__ __forceinline__ bool in_window(float rho, float mx, float my, float lo, float hi, float bound)
-{
-    return rho >= lo && rho <= hi && fmaxf(fabsf(mx), fabsf(my)) <= __fmul_rn(bound, rho);
-}
-
-// |u| of a stored cell with the fast flavour's arithmetic, guarded (collide_cell<false>'s last lines)
-__device__ __forceinline__ float speed_fast_guarded(const float c[Q])
-{
-    float r2 = c[0];
-#pragma unroll
-    for (int k = 1; k < Q; k++) r2 += c[k];
-    const float nx_ = (c[1] + c[5] + c[8]) - (c[3] + c[6] + c[7]);
-    const float ny_ = (c[2] + c[5] + c[6]) - (c[4] + c[7] + c[8]);
-    return __fdividef(speed_from_sq(fmaf(nx_, nx_, ny_ * ny_)), r2);
-}
-
-// Four cells: t -> new populations o (bounce-back applied to obstacle cells) and |u| of the new state.
-template <bool STRICT>
-__device__ __forceinline__ void collide4(const float (&t)[Q][4], uint32_t obits, float omega, float (&o)[Q][4], float (&speed)[4])
-{
-    // ---- moments of the four cells and the early window test
-    float rho[4], mx[4], my[4];
-    bool early = true;
-    if constexpr (STRICT) {
-        // SerialCode/d2q9-bgk.c:325-349: sequential density sum from 0.f, velocity brackets left to right; the four
-        // cells' chains side by side
-#pragma unroll
-        for (int j = 0; j < 4; j++) rho[j] = __fadd_rn(0.f, t[0][j]);
-#pragma unroll
-        for (int k = 1; k < Q; k++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) rho[j] = __fadd_rn(rho[j], t[k][j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        if constexpr (STRICT) {
-            mx[j] = __fsub_rn(__fadd_rn(__fadd_rn(t[1][j], t[5][j]), t[8][j]), __fadd_rn(__fadd_rn(t[3][j], t[6][j]), t[7][j]));
-            my[j] = __fsub_rn(__fadd_rn(__fadd_rn(t[2][j], t[5][j]), t[6][j]), __fadd_rn(__fadd_rn(t[4][j], t[7][j]), t[8][j]));
-        } else {
-            float d = t[0][j];
-#pragma unroll
-            for (int k = 1; k < Q; k++) d += t[k][j];
-            rho[j] = d;
-            mx[j] = (t[1][j] + t[5][j] + t[8][j]) - (t[3][j] + t[6][j] + t[7][j]);
-            my[j] = (t[2][j] + t[5][j] + t[6][j]) - (t[4][j] + t[7][j] + t[8][j]);
-        }
-        // an obstacle cell's collision is discarded: its operands may be anything
-        early = early && (in_window(rho[j], mx[j], my[j], 9.5367431640625e-07f /* 2^-20 */, 1048576.f /* 2^20 */, 2.f) || ((obits >> j) & 1u));
-    }
-    if (!early) {
-        // some fluid cell is outside the window (never in a physical flow): update_cell()'s guarded code, all four
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float tj[Q], oc[Q];
-#pragma unroll
-            for (int k = 0; k < Q; k++) tj[k] = t[k][j];
-            speed[j] = update_cell<STRICT>(tj, (obits >> j) & 1u, omega, oc);
-#pragma unroll
-            for (int k = 0; k < Q; k++) o[k][j] = oc[k];
-        }
-        return;
-    }
-    // ---- the straight block, written "vertically": every operation for IL cells before the next operation, so that
-    // the instruction stream ptxas sees already interleaves IL independent dependency chains (it keeps close to
-    // source order; cell after cell it ran each warp at the latency of one chain)
-    constexpr int IL = LBM_F2_INTERLEAVE;
-    bool late[4];
-#pragma unroll
-    for (int j0 = 0; j0 < LBM_F2_EXP_CELLS; j0 += IL) {
-        float c[IL][Q];
-        if constexpr (STRICT) {
-            // SerialCode/d2q9-bgk.c:349-401 in the reference's operation order (see update_cell for the identities)
-            float ux[IL], uy[IL], uxx[IL], uyy[IL], u_sq[IL], u5[IL], u6[IL], v[IL], q1[IL], q2[IL], q5[IL], q6[IL], s1[IL], s2[IL], s5[IL], s6[IL];
-            float w0r[IL], w1r[IL], w2r[IL];
-#pragma unroll
-            for (int i = 0; i < IL; i++) div2_unguarded(mx[j0 + i], my[j0 + i], rho[j0 + i], ux[i], uy[i]);
-#pragma unroll
-            for (int i = 0; i < IL; i++) uxx[i] = __fmul_rn(ux[i], ux[i]), uyy[i] = __fmul_rn(uy[i], uy[i]);
-#pragma unroll
-            for (int i = 0; i < IL; i++) u_sq[i] = __fadd_rn(uxx[i], uyy[i]), u5[i] = __fadd_rn(ux[i], uy[i]), u6[i] = __fsub_rn(uy[i], ux[i]);
-#pragma unroll
-            for (int i = 0; i < IL; i++) v[i] = div_const(u_sq[i], LBM_2CSQ, LBM_R_2CSQ);
-#pragma unroll
-            for (int i = 0; i < IL; i++) q1[i] = div_const(ux[i], LBM_C_SQ, LBM_R_C_SQ), q2[i] = div_const(uy[i], LBM_C_SQ, LBM_R_C_SQ);
-#pragma unroll
-            for (int i = 0; i < IL; i++) q5[i] = div_const(u5[i], LBM_C_SQ, LBM_R_C_SQ), q6[i] = div_const(u6[i], LBM_C_SQ, LBM_R_C_SQ);
-#pragma unroll
-            for (int i = 0; i < IL; i++) s1[i] = div_const(uxx[i], LBM_2CSQ2, LBM_R_2CSQ2), s2[i] = div_const(uyy[i], LBM_2CSQ2, LBM_R_2CSQ2);
-#pragma unroll
-            for (int i = 0; i < IL; i++)
-                s5[i] = div_const(__fmul_rn(u5[i], u5[i]), LBM_2CSQ2, LBM_R_2CSQ2), s6[i] = div_const(__fmul_rn(u6[i], u6[i]), LBM_2CSQ2, LBM_R_2CSQ2);
-#pragma unroll
-            for (int i = 0; i < IL; i++)
-                w0r[i] = __fmul_rn(LBM_W0, rho[j0 + i]), w1r[i] = __fmul_rn(LBM_W1, rho[j0 + i]), w2r[i] = __fmul_rn(LBM_W2, rho[j0 + i]);
-            float d[IL][Q];
-#pragma unroll
-            for (int i = 0; i < IL; i++) {
-                d[i][0] = __fmul_rn(w0r[i], __fsub_rn(1.f, v[i]));
-                d[i][1] = __fmul_rn(w1r[i], __fsub_rn(__fadd_rn(__fadd_rn(1.f, q1[i]), s1[i]), v[i]));
-                d[i][3] = __fmul_rn(w1r[i], __fsub_rn(__fadd_rn(__fsub_rn(1.f, q1[i]), s1[i]), v[i]));
-            }
-#pragma unroll
-            for (int i = 0; i < IL; i++) {
-                d[i][2] = __fmul_rn(w1r[i], __fsub_rn(__fadd_rn(__fadd_rn(1.f, q2[i]), s2[i]), v[i]));
-                d[i][4] = __fmul_rn(w1r[i], __fsub_rn(__fadd_rn(__fsub_rn(1.f, q2[i]), s2[i]), v[i]));
-            }
-#pragma unroll
-            for (int i = 0; i < IL; i++) {
-                d[i][5] = __fmul_rn(w2r[i], __fsub_rn(__fadd_rn(__fadd_rn(1.f, q5[i]), s5[i]), v[i]));
-                d[i][7] = __fmul_rn(w2r[i], __fsub_rn(__fadd_rn(__fsub_rn(1.f, q5[i]), s5[i]), v[i]));
-            }
-#pragma unroll
-            for (int i = 0; i < IL; i++) {
-                d[i][6] = __fmul_rn(w2r[i], __fsub_rn(__fadd_rn(__fadd_rn(1.f, q6[i]), s6[i]), v[i]));
-                d[i][8] = __fmul_rn(w2r[i], __fsub_rn(__fadd_rn(__fsub_rn(1.f, q6[i]), s6[i]), v[i]));
-            }
-#pragma unroll
-            for (int k = 0; k < Q; k++)
-#pragma unroll
-                for (int i = 0; i < IL; i++) c[i][k] = __fadd_rn(t[k][j0 + i], __fmul_rn(omega, __fsub_rn(d[i][k], t[k][j0 + i])));
-            // |u| of the stored values, SerialCode:425-452
-            float r2[IL], ex[IL], wx[IL], nn[IL], ss[IL];
-#pragma unroll
-            for (int i = 0; i < IL; i++) r2[i] = __fadd_rn(0.f, c[i][0]);
-#pragma unroll
-            for (int k = 1; k < Q; k++)
-#pragma unroll
-                for (int i = 0; i < IL; i++) r2[i] = __fadd_rn(r2[i], c[i][k]);
-#pragma unroll
-            for (int i = 0; i < IL; i++) {
-                ex[i] = __fadd_rn(__fadd_rn(c[i][1], c[i][5]), c[i][8]);
-                wx[i] = __fadd_rn(__fadd_rn(c[i][3], c[i][6]), c[i][7]);
-                nn[i] = __fadd_rn(__fadd_rn(c[i][2], c[i][5]), c[i][6]);
-                ss[i] = __fadd_rn(__fadd_rn(c[i][4], c[i][7]), c[i][8]);
-            }
-            float nx_[IL], ny_[IL], vx[IL], vy[IL];
-#pragma unroll
-            for (int i = 0; i < IL; i++) nx_[i] = __fsub_rn(ex[i], wx[i]), ny_[i] = __fsub_rn(nn[i], ss[i]);
-#pragma unroll
-            for (int i = 0; i < IL; i++)
-                late[j0 + i] = in_window(r2[i], nx_[i], ny_[i], 4.76837158203125e-07f /* 2^-21 */, 2097152.f /* 2^21 */, 4.f) || ((obits >> (j0 + i)) & 1u);
-#pragma unroll
-            for (int i = 0; i < IL; i++) div2_unguarded(nx_[i], ny_[i], r2[i], vx[i], vy[i]);
-#pragma unroll
-            for (int i = 0; i < IL; i++) speed[j0 + i] = speed_from_sq_select(__fadd_rn(__fmul_rn(vx[i], vx[i]), __fmul_rn(vy[i], vy[i])));
-        } else {
-#pragma unroll
-            for (int i = 0; i < IL; i++) {
-                const int j = j0 + i;
-                float ux, uy;
-                div2_unguarded(mx[j], my[j], rho[j], ux, uy);
-                const float u_sq = fmaf(ux, ux, uy * uy);
-                const float base = fmaf(-LBM_R_2CSQ, u_sq, 1.f);
-                const float u5 = ux + uy, u6 = uy - ux;
-                const float e1 = fmaf(LBM_R_2CSQ2 * ux, ux, base);
-                const float e2 = fmaf(LBM_R_2CSQ2 * uy, uy, base);
-                const float e5 = fmaf(LBM_R_2CSQ2 * u5, u5, base);
-                const float e6 = fmaf(LBM_R_2CSQ2 * u6, u6, base);
-                const float w0r = LBM_W0 * rho[j], w1r = LBM_W1 * rho[j], w2r = LBM_W2 * rho[j];
-                float d[Q];
-                d[0] = w0r * base;
-                d[1] = w1r * fmaf(LBM_R_C_SQ, ux, e1);
-                d[3] = w1r * fmaf(-LBM_R_C_SQ, ux, e1);
-                d[2] = w1r * fmaf(LBM_R_C_SQ, uy, e2);
-                d[4] = w1r * fmaf(-LBM_R_C_SQ, uy, e2);
-                d[5] = w2r * fmaf(LBM_R_C_SQ, u5, e5);
-                d[7] = w2r * fmaf(-LBM_R_C_SQ, u5, e5);
-                d[6] = w2r * fmaf(LBM_R_C_SQ, u6, e6);
-                d[8] = w2r * fmaf(-LBM_R_C_SQ, u6, e6);
-#pragma unroll
-                for (int k = 0; k < Q; k++) c[i][k] = fmaf(omega, d[k] - t[k][j], t[k][j]);
-                float r2 = c[i][0];
-#pragma unroll
-                for (int k = 1; k < Q; k++) r2 += c[i][k];
-                const float nx_ = (c[i][1] + c[i][5] + c[i][8]) - (c[i][3] + c[i][6] + c[i][7]);
-                const float ny_ = (c[i][2] + c[i][5] + c[i][6]) - (c[i][4] + c[i][7] + c[i][8]);
-                late[j] = in_window(r2, nx_, ny_, 4.76837158203125e-07f, 2097152.f, 4.f) || ((obits >> j) & 1u);
-                speed[j] = __fdividef(speed_from_sq_select(fmaf(nx_, nx_, ny_ * ny_)), r2);
-            }
-        }
-        // obstacle: bounce-back permutation, SerialCode/d2q9-bgk.c:287-299 (speed 0 keeps the streamed value); selected
-        // here, per group of cells, so that the streamed-in values die early instead of living to the end of the block
-#pragma unroll
-        for (int i = 0; i < IL; i++) {
-            const int j = j0 + i;
-            const bool solid = (obits >> j) & 1u;
-            o[0][j] = solid ? t[0][j] : c[i][0];
-            o[1][j] = solid ? t[3][j] : c[i][1];
-            o[2][j] = solid ? t[4][j] : c[i][2];
-            o[3][j] = solid ? t[1][j] : c[i][3];
-            o[4][j] = solid ? t[2][j] : c[i][4];
-            o[5][j] = solid ? t[7][j] : c[i][5];
-            o[6][j] = solid ? t[8][j] : c[i][6];
-            o[7][j] = solid ? t[5][j] : c[i][7];
-            o[8][j] = solid ? t[6][j] : c[i][8];
-        }
-    }
-#pragma unroll
-    for (int j = LBM_F2_EXP_CELLS; j < 4; j++) { // diagnostics only
-        late[j] = true, speed[j] = 0.f;
-#pragma unroll
-        for (int k = 0; k < Q; k++) o[k][j] = t[k][j];
-    }
-    // ---- the new populations are exact; a |u| whose operands left the late window is redone with the guarded code
-    if (!(late[0] && late[1] && late[2] && late[3])) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (!late[j]) {
-                float cj[Q];
-#pragma unroll
-                for (int k = 0; k < Q; k++) cj[k] = o[k][j];
-                if constexpr (STRICT) speed[j] = speed_strict(cj);
-                else speed[j] = speed_fast_guarded(cj);
-            }
-        }
-    }
 }
 
 // update4() for this kernel: collide4, the |u| of the four cells straight into one 64-bit total (any split into the
@@ -456,38 +198,7 @@ __device__ __forceinline__ void f2_load_plane_any(int k, const Fused2Args& a, fl
 // that ends its phase 0 (every warp then holds its row in registers), so the copy of iteration c + NSTAGES*SROWS/R
 // runs behind phase 1 of iteration c and everything after it.  16 warps per SM (2 CTAs of 8, or 1 of 16) is four per
 // scheduler: 128 registers per thread.
-//
-// FLAGS: no CTA barrier in the marching loop.  Phase 1 of row q-1 only needs rows q-2, q-1, q of the ring, i.e. the
-// phase-0 results of this warp and of the two warps before it; phase 0 of row q overwrites the ring slot of row
-// q-R-2, which only the phase 1 of this warp and of the two before it read.  So each warp publishes two counters
-// in shared memory (phase-0 / phase-1 rows finished) and polls its two predecessors' instead of stopping the
-// whole CTA twice per iteration (with barriers, "barrier" was the top stall reason: every warp waited for the
-// slowest of eight, four times per pair of rows).  A stage is refilled by the LAST of its SROWS reader warps
-// (a counter per stage), right after that warp has its row in registers.
-__device__ __forceinline__ int lds_volatile(const int* p)
-{
-    int v;
-    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
-}
-__device__ __forceinline__ void poll_at_least(const int* p, int need)
-{
-    while (lds_volatile(p) < need) {
-    }
-}
-// lane 0 publishes `value` once every lane of the warp has got here.  FENCE: the lanes' earlier shared-memory
-// stores must be visible before the counter (phase 0: the ring row).  Without it (phase 1: only LOADS of the ring
-// precede, and their values have long been consumed by the arithmetic; a fence here would also wait for the
-// phase's global stores to drain).
-template <bool FENCE>
-__device__ __forceinline__ void post(int* p, int value, int lane)
-{
-    if constexpr (FENCE) __threadfence_block();
-    __syncwarp();
-    if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(value) : "memory");
-}
-
-template <bool STRICT, int R, int SROWS, int NSTAGES, int MINB, bool FLAGS>
+template <bool STRICT, int R, int SROWS, int NSTAGES, int MINB>
 __global__ void __launch_bounds__(32 * R, MINB)
     step2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapw, const Fused2Args a)
 {
@@ -503,7 +214,6 @@ __global__ void __launch_bounds__(32 * R, MINB)
     const uint32_t buf2_s = stages_s + NSTAGES * STAGE * 4;        // [RB][Q][128] floats (+ a few floats of slack)
     __shared__ __align__(8) uint64_t full_bar[NSTAGES];
     __shared__ unsigned long long s_acc[2][3];
-    __shared__ int s_done0[R], s_done1[R];             // FLAGS: iterations whose phase 0 / phase 1 each warp has finished
     __shared__ unsigned s_readers[NSTAGES];            // warps that have read the stage into registers
 
     const int tid = threadIdx.x;
@@ -514,7 +224,6 @@ __global__ void __launch_bounds__(32 * R, MINB)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 6) s_acc[tid / 3][tid % 3] = 0ull;
-    if (tid < R) s_done0[tid] = 0, s_done1[tid] = 0;
     if (tid < NSTAGES) s_readers[tid] = 0u;
     __syncthreads();
 
@@ -526,7 +235,6 @@ __global__ void __launch_bounds__(32 * R, MINB)
     unsigned long long acc_a = 0ull, acc_b = 0ull;     // per-thread |u| totals (units of 2^-40) of step t1 / t1+1
     unsigned bad_a = 0u, bad_b = 0u;
     int nbase = 0;                                     // TMA stages consumed by this CTA's earlier units
-    int itbase = 0;                                    // FLAGS: iterations of this CTA's earlier units
     bool primed = false;                               // the TMA pipeline has been started
     // request stage number `seq` of this CTA's stage sequence (the current unit starts at sequence number
     // nbase_cur and has nst_cur stages; the units after it are u_cur + gridDim.x, ...)
@@ -557,13 +265,6 @@ __global__ void __launch_bounds__(32 * R, MINB)
         const int nst = (rows1 + SROWS - 1) / SROWS;
         const int nc = (rows1 + R - 1) / R;
         const bool tma_unit = un.kind == 2;
-        if constexpr (FLAGS) {
-            // the ring and the stage buffers are reused from row 0: every warp must have left the previous unit
-            if (itbase > 0) {
-#pragma unroll 1
-                for (int k = 0; k < R; k++) poll_at_least(&s_done1[k], itbase);
-            }
-        }
         if (!tma_unit) {
             // boundary unit (always ahead of this CTA's interior units): four rows into stage buffer 0 with ordinary
             // loads, after the neighbour has delivered the rows of this epoch
@@ -668,24 +369,6 @@ __global__ void __launch_bounds__(32 * R, MINB)
                             }
                         }
                     }
-                    if constexpr (FLAGS) {
-                        // the ring slot of row q held row q-R-2: its readers were the phase 1 of rows q-R-2 and q-R-1
-                        // (other warps) and q-R (this warp)
-#pragma unroll
-                        for (int dq = 2; dq >= 1; dq--) {
-                            const int qq = q - R - dq;
-                            if (qq >= 0) poll_at_least(&s_done1[qq % R], itbase + qq / R + 1);
-                        }
-                    }
-                } else {
-                    if constexpr (FLAGS) {
-                        // rows q-2, q-1 of the ring come from the phase 0 of the two warps before this one
-#pragma unroll
-                        for (int dq = 2; dq >= 1; dq--) {
-                            const int qq = q - dq;
-                            if (qq >= 0) poll_at_least(&s_done0[qq % R], itbase + qq / R + 1);
-                        }
-                    }
                 }
                 if (phase == 1 && active) {
                     // ring rows of the intermediate step: plane k comes from row rel - cy_k, column x - cx_k
@@ -773,23 +456,13 @@ __global__ void __launch_bounds__(32 * R, MINB)
                         }
                     }
                 }
-                if constexpr (FLAGS) {
-                    if (phase == 0) {
-                        post<true>(&s_done0[warp], itbase + c + 1, lane);
-                    } else {
-                        post<false>(&s_done1[warp], itbase + c + 1, lane);
-                    }
-                    if (!tma_unit) __syncthreads(); // boundary units (one iteration, rare) keep the CTA barriers
-                } else {
-                    // phase 0 -> 1: the ring rows are complete and every warp holds its staged row in registers;
-                    // phase 1 -> next iteration: the ring rows may be overwritten
-                    __syncthreads();
-                }
+                // phase 0 -> 1: the ring rows are complete and every warp holds its staged row in registers;
+                // phase 1 -> next iteration: the ring rows may be overwritten
+                __syncthreads();
             }
         }
         if (!tma_unit && a.h.on && tid == 0) halo_arrive(a.h, un.kind == 0, un.kind == 1, static_cast<unsigned>(a.nsx));
         if (tma_unit) nbase += nst;
-        itbase += nc;
     }
 
     // ---------------- |u| sums of both steps: one reduction per launch ----------------

@@ -112,6 +112,14 @@ def test_division_and_sqrt_sequences_match_the_ieee_instructions(gpu, pkg):
         assert pkg.selftest(pairs=1 << 31, seed=seed) == (0, 0)
 
 
+def test_packed_collision_equals_the_scalar_cell_code(gpu, pkg):
+    """The four-cell collision of the step kernels (FADD2 / FMUL2 / FFMA2, one basic block) against update_cell()
+    (scalar instructions, guarded IEEE paths) on 2 x 2^24 random groups of four cells: strict flavour bit for bit
+    (populations and |u|) -- in particular the toolchain has not contracted a packed multiply with a packed add."""
+    for seed in (1, 2):
+        assert pkg.selftest_collide("strict", sets=1 << 24, seed=seed) == (0, 0)
+
+
 def test_chunked_runs_equal_one_run(gpu, pkg, orc):
     """lbm_run may be called repeatedly: 3+1+40+33 steps (graph replays and single launches, odd and
     even chunk lengths) == 77 steps, and the accelerate-at-store folding never leaks across calls."""
