@@ -7,7 +7,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-_LIB = os.path.join(_HERE, "liblbm_b200.so")
+_LIB = os.environ.get("LBM_B200_LIB") or os.path.join(_HERE, "liblbm_b200.so")  # override: tuning builds (tools/variants.sh)
 
 NSPEEDS = 9
 HALO_HANDLE_BYTES = 128

@@ -216,6 +216,9 @@ bool tma_by_shape(int ty, int stages, int minb, TmaChoice* c)
     LBM_TMA_CASE(4, 4, 3)
     LBM_TMA_CASE(4, 6, 2)
     LBM_TMA_CASE(16, 2, 1)
+    LBM_TMA_CASE(15, 2, 1)
+    LBM_TMA_CASE(7, 3, 2)
+    LBM_TMA_CASE(7, 4, 2)
     LBM_TMA_CASE(16, 3, 1)
 #undef LBM_TMA_CASE
     return false;

@@ -11,10 +11,10 @@
 // of the stream takes half the issue slots.  Cells 0,1 of a thread form one pair, cells 2,3 the other; a 128-bit
 // shared-memory or global load of four consecutive cells lands in two aligned pairs as it is.
 //
-// Structure (as before, now per pair): update_cell() guards each of its special sequences (division by rho, the
+// Structure (per pair): update_cell() guards each of its special sequences (division by rho, the
 // constant divisions, the square root) with its own test and branch; ptxas schedules within basic blocks, so here the
-// moments of the four cells are formed first and tested against an "early" window; a thread with a cell outside it
-// (never in a physical flow) takes update_cell()'s guarded code for its four cells; everybody else runs the sequences
+// moments of the pair are formed first and tested against an "early" window; a thread with a cell outside it
+// (never in a physical flow) takes update_cell()'s guarded code for the pair; everybody else runs the sequences
 // unguarded in one block, and a "late" window test on the new populations decides whether the |u| of a cell has to be
 // redone with the guarded code (the new populations themselves are exact by then).  Windows:
 //   early: 2^-20 <= rho <= 2^20 and max(|m_x|, |m_y|) <= 2 rho  (so |u| <~ 2)
@@ -25,6 +25,7 @@
 //             and the result is 0 below (a select, as in speed_from_sq).
 // NaN operands fail both tests.  The fast flavour uses the same structure around its own arithmetic.
 #pragma once
+
 
 namespace lbm {
 
@@ -81,44 +82,122 @@ __device__ __forceinline__ f2 neg2(f2 a)
 
 __device__ __forceinline__ f2 mul2_rounded(f2 a, f2 b) { return fma2(a, b, bc2(c_negzero)); }
 
-// a1 / b and a2 / b on both halves: div2_rn()'s sequence without its operand test (the caller's window implies it)
-__device__ __forceinline__ void div2_pair(f2 a1, f2 a2, f2 b, f2& q1, f2& q2)
+// ---- NP pairs side by side ("vertical" code) --------------------------------------------------------------------
+// Every operation below is written for NP pairs at once, so the instruction stream ptxas sees already interleaves NP
+// independent dependency chains (it keeps close to source order, and the collision is one long chain: density sum ->
+// division -> equilibrium -> relaxation -> density sum -> division -> square root).  With 16 warps per SM the kernels
+// are bound by exactly that latency; one pair after the other measured 5-10 % slower than two side by side.
+template <int NP>
+struct PV {
+    f2 v[NP];
+};
+#define LBM_PV_OP2(name, expr)                                                      \
+    template <int NP>                                                               \
+    __device__ __forceinline__ PV<NP> name(const PV<NP>& a, const PV<NP>& b)        \
+    {                                                                               \
+        PV<NP> r;                                                                   \
+        _Pragma("unroll") for (int h = 0; h < NP; h++) r.v[h] = expr;               \
+        return r;                                                                   \
+    }
+LBM_PV_OP2(vadd, add2(a.v[h], b.v[h]))
+LBM_PV_OP2(vsub, sub2(a.v[h], b.v[h]))
+LBM_PV_OP2(vmul, mul2(a.v[h], b.v[h]))
+LBM_PV_OP2(vmul_rounded, mul2_rounded(a.v[h], b.v[h]))
+#undef LBM_PV_OP2
+template <int NP>
+__device__ __forceinline__ PV<NP> vfma(const PV<NP>& a, const PV<NP>& b, const PV<NP>& c)
 {
-    float b0, b1, y00, y01;
-    upk(b, b0, b1);
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y00) : "f"(b0));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y01) : "f"(b1));
-    const f2 y0 = pk(y00, y01), nb = neg2(b);
-    const f2 e = fma2(nb, y0, bc2(1.f));
-    const f2 y = fma2(y0, e, y0);
-    const f2 p1 = mul2(a1, y), p2 = mul2(a2, y);
-    q1 = fma2(y, fma2(nb, p1, a1), p1);
-    q2 = fma2(y, fma2(nb, p2, a2), p2);
+    PV<NP> r;
+#pragma unroll
+    for (int h = 0; h < NP; h++) r.v[h] = fma2(a.v[h], b.v[h], c.v[h]);
+    return r;
 }
-// div_const() on both halves; nc = -c:  fma(-q, c, x) == fma(q, -c, x) (the product is exact either way)
-__device__ __forceinline__ f2 div_const2(f2 x, float c, float rc)
+template <int NP>
+__device__ __forceinline__ PV<NP> vneg(const PV<NP>& a)
 {
-    const f2 q = mul2(x, bc2(rc));
-    const f2 r = fma2(q, bc2(-c), x);
-    return fma2(r, bc2(rc), q);
+    PV<NP> r;
+#pragma unroll
+    for (int h = 0; h < NP; h++) r.v[h] = neg2(a.v[h]);
+    return r;
 }
-// speed_from_sq()'s sequence on both halves, a select instead of its range test
-__device__ __forceinline__ void speed_from_sq_pair(f2 x, float& s0, float& s1)
+template <int NP>
+__device__ __forceinline__ PV<NP> vbc(float c)
 {
-    float x0, x1, y0, y1;
-    upk(x, x0, x1);
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(x0));
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(x1));
-    const f2 y = pk(y0, y1);
-    const f2 g = mul2(x, y), h = mul2(y, bc2(0.5f));
-    const f2 s = fma2(fma2(neg2(g), g, x), h, g);
-    upk(s, s0, s1);
-    s0 = x0 >= 7.888609052210118e-31f /* 2^-100 */ ? s0 : 0.f;
-    s1 = x1 >= 7.888609052210118e-31f ? s1 : 0.f;
+    PV<NP> r;
+#pragma unroll
+    for (int h = 0; h < NP; h++) r.v[h] = bc2(c);
+    return r;
+}
+
+// a1 / b and a2 / b: div2_rn()'s sequence without its operand test (the caller's window implies it)
+template <int NP>
+__device__ __forceinline__ void vdiv2(const PV<NP>& a1, const PV<NP>& a2, const PV<NP>& b, PV<NP>& q1, PV<NP>& q2)
+{
+    PV<NP> y0;
+#pragma unroll
+    for (int h = 0; h < NP; h++) {
+        float b0, b1, y00, y01;
+        upk(b.v[h], b0, b1);
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y00) : "f"(b0));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y01) : "f"(b1));
+        y0.v[h] = pk(y00, y01);
+    }
+    const PV<NP> nb = vneg(b);
+    const PV<NP> e = vfma(nb, y0, vbc<NP>(1.f));
+    const PV<NP> y = vfma(y0, e, y0);
+    const PV<NP> p1 = vmul(a1, y), p2 = vmul(a2, y);
+    q1 = vfma(y, vfma(nb, p1, a1), p1);
+    q2 = vfma(y, vfma(nb, p2, a2), p2);
+}
+// div_const():  fma(-q, c, x) == fma(q, -c, x) (the product is exact either way)
+template <int NP>
+__device__ __forceinline__ PV<NP> vdiv_const(const PV<NP>& x, float c, float rc)
+{
+    const PV<NP> q = vmul(x, vbc<NP>(rc));
+    const PV<NP> r = vfma(q, vbc<NP>(-c), x);
+    return vfma(r, vbc<NP>(rc), q);
+}
+// speed_from_sq()'s sequence, a select instead of its range test; s[2h], s[2h+1] = the roots of pair h
+template <int NP>
+__device__ __forceinline__ void vspeed_from_sq(const PV<NP>& x, float (&s)[2 * NP])
+{
+    PV<NP> y;
+#pragma unroll
+    for (int h = 0; h < NP; h++) {
+        float x0, x1, y0, y1;
+        upk(x.v[h], x0, x1);
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(x0));
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(x1));
+        y.v[h] = pk(y0, y1);
+    }
+    const PV<NP> g = vmul(x, y), hh = vmul(y, vbc<NP>(0.5f));
+    const PV<NP> r = vfma(vfma(vneg(g), g, x), hh, g);
+#pragma unroll
+    for (int h = 0; h < NP; h++) {
+        float x0, x1, r0, r1;
+        upk(x.v[h], x0, x1), upk(r.v[h], r0, r1);
+        s[2 * h] = x0 >= 7.888609052210118e-31f /* 2^-100 */ ? r0 : 0.f;
+        s[2 * h + 1] = x1 >= 7.888609052210118e-31f ? r1 : 0.f;
+    }
 }
 __device__ __forceinline__ bool in_window(float rho, float mx, float my, float lo, float hi, float bound)
 {
     return (rho >= lo) & (rho <= hi) & (fmaxf(fabsf(mx), fabsf(my)) <= __fmul_rn(bound, rho)); // no short circuit: no branches
+}
+// all cells of the NP pairs inside the window, obstacle cells (bit j of solid) excepted
+template <int NP>
+__device__ __forceinline__ bool all_in_window(const PV<NP>& rho, const PV<NP>& mx, const PV<NP>& my, uint32_t solid, float lo, float hi,
+                                              float bound)
+{
+    bool ok = true;
+#pragma unroll
+    for (int h = 0; h < NP; h++) {
+        float r0, r1, a0, a1, b0, b1;
+        upk(rho.v[h], r0, r1), upk(mx.v[h], a0, a1), upk(my.v[h], b0, b1);
+        ok = ok & (in_window(r0, a0, b0, lo, hi, bound) | (((solid >> (2 * h)) & 1u) != 0)) &
+             (in_window(r1, a1, b1, lo, hi, bound) | (((solid >> (2 * h + 1)) & 1u) != 0));
+    }
+    return ok;
 }
 
 // |u| of a stored cell with the fast flavour's arithmetic, guarded (collide_cell<false>'s last lines)
@@ -132,95 +211,132 @@ __device__ __forceinline__ float speed_fast_guarded(const float c[Q])
     return __fdividef(speed_from_sq(fmaf(nx_, nx_, ny_ * ny_)), r2);
 }
 
-// rho and the momentum of a pair of cells; STRICT: SerialCode/d2q9-bgk.c:325-349 (sequential density sum from 0.f,
-// velocity brackets left to right)
-template <bool STRICT>
-__device__ __forceinline__ void moments_pair(const f2 (&t)[Q], f2& rho, f2& mx, f2& my)
+// rho and the momentum; STRICT: SerialCode/d2q9-bgk.c:325-349 (sequential density sum from 0.f, velocity brackets
+// left to right)
+template <bool STRICT, int NP>
+__device__ __forceinline__ void vmoments(const PV<NP> (&t)[Q], PV<NP>& rho, PV<NP>& mx, PV<NP>& my)
 {
-    f2 d = STRICT ? add2(bc2(0.f), t[0]) : t[0];
+    PV<NP> d = STRICT ? vadd(vbc<NP>(0.f), t[0]) : t[0];
 #pragma unroll
-    for (int k = 1; k < Q; k++) d = add2(d, t[k]);
+    for (int k = 1; k < Q; k++) d = vadd(d, t[k]);
     rho = d;
-    mx = sub2(add2(add2(t[1], t[5]), t[8]), add2(add2(t[3], t[6]), t[7]));
-    my = sub2(add2(add2(t[2], t[5]), t[6]), add2(add2(t[4], t[7]), t[8]));
+    mx = vsub(vadd(vadd(t[1], t[5]), t[8]), vadd(vadd(t[3], t[6]), t[7]));
+    my = vsub(vadd(vadd(t[2], t[5]), t[6]), vadd(vadd(t[4], t[7]), t[8]));
 }
 
-// BGK relaxation of a pair of fluid cells inside the early window: t -> c, plus the moments of c
-template <bool STRICT>
-__device__ __forceinline__ void relax_pair(const f2 (&t)[Q], f2 rho, f2 mx, f2 my, float omega, f2 (&c)[Q])
+// BGK relaxation of fluid cells inside the early window: t -> c
+template <bool STRICT, int NP>
+__device__ __forceinline__ void vrelax(const PV<NP> (&t)[Q], const PV<NP>& rho, const PV<NP>& mx, const PV<NP>& my, float omega,
+                                       PV<NP> (&c)[Q])
 {
-    f2 ux, uy;
-    div2_pair(mx, my, rho, ux, uy);
-    const f2 one = bc2(1.f), om = bc2(omega);
-    f2 d[Q];
+    PV<NP> ux, uy;
+    vdiv2(mx, my, rho, ux, uy);
+    const PV<NP> one = vbc<NP>(1.f), om = vbc<NP>(omega);
+    PV<NP> d[Q];
     if constexpr (STRICT) {
         // SerialCode/d2q9-bgk.c:349-401 in the reference's operation order (see collide_cell for the identities)
-        const f2 uxx = mul2_rounded(ux, ux), uyy = mul2_rounded(uy, uy);
-        const f2 u_sq = add2(uxx, uyy);
-        const f2 u5 = add2(ux, uy), u6 = sub2(uy, ux);
-        const f2 v = div_const2(u_sq, LBM_2CSQ, LBM_R_2CSQ);
-        const f2 q1 = div_const2(ux, LBM_C_SQ, LBM_R_C_SQ), q2 = div_const2(uy, LBM_C_SQ, LBM_R_C_SQ);
-        const f2 q5 = div_const2(u5, LBM_C_SQ, LBM_R_C_SQ), q6 = div_const2(u6, LBM_C_SQ, LBM_R_C_SQ);
-        const f2 s1 = div_const2(uxx, LBM_2CSQ2, LBM_R_2CSQ2), s2 = div_const2(uyy, LBM_2CSQ2, LBM_R_2CSQ2);
-        const f2 s5 = div_const2(mul2(u5, u5), LBM_2CSQ2, LBM_R_2CSQ2), s6 = div_const2(mul2(u6, u6), LBM_2CSQ2, LBM_R_2CSQ2);
-        const f2 w0r = mul2(bc2(LBM_W0), rho), w1r = mul2(bc2(LBM_W1), rho), w2r = mul2(bc2(LBM_W2), rho);
-        d[0] = mul2_rounded(w0r, sub2(one, v));
-        d[1] = mul2_rounded(w1r, sub2(add2(add2(one, q1), s1), v));
-        d[3] = mul2_rounded(w1r, sub2(add2(sub2(one, q1), s1), v));
-        d[2] = mul2_rounded(w1r, sub2(add2(add2(one, q2), s2), v));
-        d[4] = mul2_rounded(w1r, sub2(add2(sub2(one, q2), s2), v));
-        d[5] = mul2_rounded(w2r, sub2(add2(add2(one, q5), s5), v));
-        d[7] = mul2_rounded(w2r, sub2(add2(sub2(one, q5), s5), v));
-        d[6] = mul2_rounded(w2r, sub2(add2(add2(one, q6), s6), v));
-        d[8] = mul2_rounded(w2r, sub2(add2(sub2(one, q6), s6), v));
+        const PV<NP> uxx = vmul_rounded(ux, ux), uyy = vmul_rounded(uy, uy);
+        const PV<NP> u_sq = vadd(uxx, uyy);
+        const PV<NP> u5 = vadd(ux, uy), u6 = vsub(uy, ux);
+        const PV<NP> v = vdiv_const(u_sq, LBM_2CSQ, LBM_R_2CSQ);
+        const PV<NP> q1 = vdiv_const(ux, LBM_C_SQ, LBM_R_C_SQ), q2 = vdiv_const(uy, LBM_C_SQ, LBM_R_C_SQ);
+        const PV<NP> q5 = vdiv_const(u5, LBM_C_SQ, LBM_R_C_SQ), q6 = vdiv_const(u6, LBM_C_SQ, LBM_R_C_SQ);
+        const PV<NP> s1 = vdiv_const(uxx, LBM_2CSQ2, LBM_R_2CSQ2), s2 = vdiv_const(uyy, LBM_2CSQ2, LBM_R_2CSQ2);
+        const PV<NP> s5 = vdiv_const(vmul(u5, u5), LBM_2CSQ2, LBM_R_2CSQ2), s6 = vdiv_const(vmul(u6, u6), LBM_2CSQ2, LBM_R_2CSQ2);
+        const PV<NP> w0r = vmul(vbc<NP>(LBM_W0), rho), w1r = vmul(vbc<NP>(LBM_W1), rho), w2r = vmul(vbc<NP>(LBM_W2), rho);
+        d[0] = vmul_rounded(w0r, vsub(one, v));
+        d[1] = vmul_rounded(w1r, vsub(vadd(vadd(one, q1), s1), v));
+        d[3] = vmul_rounded(w1r, vsub(vadd(vsub(one, q1), s1), v));
+        d[2] = vmul_rounded(w1r, vsub(vadd(vadd(one, q2), s2), v));
+        d[4] = vmul_rounded(w1r, vsub(vadd(vsub(one, q2), s2), v));
+        d[5] = vmul_rounded(w2r, vsub(vadd(vadd(one, q5), s5), v));
+        d[7] = vmul_rounded(w2r, vsub(vadd(vsub(one, q5), s5), v));
+        d[6] = vmul_rounded(w2r, vsub(vadd(vadd(one, q6), s6), v));
+        d[8] = vmul_rounded(w2r, vsub(vadd(vsub(one, q6), s6), v));
 #pragma unroll
-        for (int k = 0; k < Q; k++) c[k] = add2(t[k], mul2_rounded(om, sub2(d[k], t[k])));
+        for (int k = 0; k < Q; k++) c[k] = vadd(t[k], vmul_rounded(om, vsub(d[k], t[k])));
     } else {
         // collide_cell<false>'s formula: fused multiply-adds, multiplications by RN(1/c)
-        const f2 u_sq = fma2(ux, ux, mul2(uy, uy));
-        const f2 base = fma2(bc2(-LBM_R_2CSQ), u_sq, one);
-        const f2 u5 = add2(ux, uy), u6 = sub2(uy, ux);
-        const f2 k2 = bc2(LBM_R_2CSQ2), k1 = bc2(LBM_R_C_SQ), nk1 = bc2(-LBM_R_C_SQ);
-        const f2 e1 = fma2(mul2(k2, ux), ux, base);
-        const f2 e2 = fma2(mul2(k2, uy), uy, base);
-        const f2 e5 = fma2(mul2(k2, u5), u5, base);
-        const f2 e6 = fma2(mul2(k2, u6), u6, base);
-        const f2 w0r = mul2(bc2(LBM_W0), rho), w1r = mul2(bc2(LBM_W1), rho), w2r = mul2(bc2(LBM_W2), rho);
-        d[0] = mul2(w0r, base);
-        d[1] = mul2(w1r, fma2(k1, ux, e1));
-        d[3] = mul2(w1r, fma2(nk1, ux, e1));
-        d[2] = mul2(w1r, fma2(k1, uy, e2));
-        d[4] = mul2(w1r, fma2(nk1, uy, e2));
-        d[5] = mul2(w2r, fma2(k1, u5, e5));
-        d[7] = mul2(w2r, fma2(nk1, u5, e5));
-        d[6] = mul2(w2r, fma2(k1, u6, e6));
-        d[8] = mul2(w2r, fma2(nk1, u6, e6));
+        const PV<NP> u_sq = vfma(ux, ux, vmul(uy, uy));
+        const PV<NP> base = vfma(vbc<NP>(-LBM_R_2CSQ), u_sq, one);
+        const PV<NP> u5 = vadd(ux, uy), u6 = vsub(uy, ux);
+        const PV<NP> k2 = vbc<NP>(LBM_R_2CSQ2), k1 = vbc<NP>(LBM_R_C_SQ), nk1 = vbc<NP>(-LBM_R_C_SQ);
+        const PV<NP> e1 = vfma(vmul(k2, ux), ux, base);
+        const PV<NP> e2 = vfma(vmul(k2, uy), uy, base);
+        const PV<NP> e5 = vfma(vmul(k2, u5), u5, base);
+        const PV<NP> e6 = vfma(vmul(k2, u6), u6, base);
+        const PV<NP> w0r = vmul(vbc<NP>(LBM_W0), rho), w1r = vmul(vbc<NP>(LBM_W1), rho), w2r = vmul(vbc<NP>(LBM_W2), rho);
+        d[0] = vmul(w0r, base);
+        d[1] = vmul(w1r, vfma(k1, ux, e1));
+        d[3] = vmul(w1r, vfma(nk1, ux, e1));
+        d[2] = vmul(w1r, vfma(k1, uy, e2));
+        d[4] = vmul(w1r, vfma(nk1, uy, e2));
+        d[5] = vmul(w2r, vfma(k1, u5, e5));
+        d[7] = vmul(w2r, vfma(nk1, u5, e5));
+        d[6] = vmul(w2r, vfma(k1, u6, e6));
+        d[8] = vmul(w2r, vfma(nk1, u6, e6));
 #pragma unroll
-        for (int k = 0; k < Q; k++) c[k] = fma2(om, sub2(d[k], t[k]), t[k]);
+        for (int k = 0; k < Q; k++) c[k] = vfma(om, vsub(d[k], t[k]), t[k]);
     }
 }
 
-// Four cells: t[k][j] = what cell j pulls from plane k  ->  new populations o (bounce-back applied to obstacle cells,
-// SerialCode/d2q9-bgk.c:287-299) and |u| of the new state (SerialCode:425-452; garbage for obstacle cells, which
-// the callers do not count).
-template <bool STRICT>
+// the part of the collision after the early window test, for NP pairs side by side: relaxation, bounce-back select,
+// |u| of the new state; returns false if a cell left the late window (its |u| has to be redone by the caller)
+template <bool STRICT, int NP>
+__device__ __forceinline__ bool collide_block(const PV<NP> (&t)[Q], const PV<NP>& rho, const PV<NP>& mx, const PV<NP>& my, uint32_t obits,
+                                              float omega, PV<NP> (&o)[Q], float (&speed)[2 * NP])
+{
+    constexpr int mirror[Q] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+    PV<NP> c[Q];
+    vrelax<STRICT>(t, rho, mx, my, omega, c);
+    // |u| of the stored values
+    PV<NP> r2, nx_, ny_;
+    vmoments<STRICT>(c, r2, nx_, ny_);
+    const bool late = all_in_window(r2, nx_, ny_, obits, 4.76837158203125e-07f /* 2^-21 */, 2097152.f /* 2^21 */, 4.f);
+    if constexpr (STRICT) {
+        PV<NP> vx, vy;
+        vdiv2(nx_, ny_, r2, vx, vy);
+        vspeed_from_sq(vadd(vmul_rounded(vx, vx), vmul_rounded(vy, vy)), speed);
+    } else {
+        vspeed_from_sq(vfma(nx_, nx_, vmul(ny_, ny_)), speed);
+#pragma unroll
+        for (int h = 0; h < NP; h++) {
+            float r0, r1;
+            upk(r2.v[h], r0, r1);
+            speed[2 * h] = __fdividef(speed[2 * h], r0), speed[2 * h + 1] = __fdividef(speed[2 * h + 1], r1);
+        }
+    }
+    // obstacle: bounce-back permutation (speed 0 keeps the streamed value)
+#pragma unroll
+    for (int h = 0; h < NP; h++) {
+        const bool solid0 = (obits >> (2 * h)) & 1u, solid1 = (obits >> (2 * h + 1)) & 1u;
+#pragma unroll
+        for (int k = 0; k < Q; k++) {
+            float c0, c1, m0, m1;
+            upk(c[k].v[h], c0, c1);
+            upk(t[mirror[k]].v[h], m0, m1);
+            o[k].v[h] = pk(solid0 ? m0 : c0, solid1 ? m1 : c1);
+        }
+    }
+    return late;
+}
+
+// Four cells of a thread: t[k][j] = what cell j pulls from plane k (cells 0,1 and 2,3 form the two pairs)  ->  new
+// populations o (bounce-back applied to obstacle cells, SerialCode/d2q9-bgk.c:287-299) and |u| of the new state
+// (SerialCode:425-452; garbage for obstacle cells, which the callers do not count).
+// VERT: both pairs side by side through every operation (more registers: kernels with >= 130 of them), otherwise
+// one pair after the other -- still one basic block, so ptxas overlaps the end of the first with the start of the second.
+template <bool STRICT, bool VERT>
 __device__ __forceinline__ void collide4(const float (&t)[Q][4], uint32_t obits, float omega, float (&o)[Q][4], float (&speed)[4])
 {
-    f2 tp[2][Q], rho[2], mx[2], my[2];
-    bool early = true;
+    obits &= 0xfu;
+    PV<2> tp[Q], rho, mx, my;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-#pragma unroll
-        for (int k = 0; k < Q; k++) tp[h][k] = pk(t[k][2 * h], t[k][2 * h + 1]);
-        moments_pair<STRICT>(tp[h], rho[h], mx[h], my[h]);
-        float r0, r1, a0, a1, b0, b1;
-        upk(rho[h], r0, r1), upk(mx[h], a0, a1), upk(my[h], b0, b1);
-        // an obstacle cell's collision is discarded: its operands may be anything
-        early = early & (in_window(r0, a0, b0, 9.5367431640625e-07f /* 2^-20 */, 1048576.f /* 2^20 */, 2.f) | (((obits >> (2 * h)) & 1u) != 0)) &
-                (in_window(r1, a1, b1, 9.5367431640625e-07f, 1048576.f, 2.f) | (((obits >> (2 * h + 1)) & 1u) != 0));
-    }
-    if (!early) {
-        // some fluid cell is outside the window (never in a physical flow): update_cell()'s guarded code, all four
+    for (int k = 0; k < Q; k++) tp[k].v[0] = pk(t[k][0], t[k][1]), tp[k].v[1] = pk(t[k][2], t[k][3]);
+    vmoments<STRICT>(tp, rho, mx, my);
+    // an obstacle cell's collision is discarded: its operands may be anything
+    if (!all_in_window(rho, mx, my, obits, 9.5367431640625e-07f /* 2^-20 */, 1048576.f /* 2^20 */, 2.f)) {
+        // a fluid cell is outside the window (never in a physical flow): update_cell()'s guarded code, all four
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             float tj[Q], oc[Q];
@@ -232,40 +348,28 @@ __device__ __forceinline__ void collide4(const float (&t)[Q][4], uint32_t obits,
         }
         return;
     }
-    bool late = true;
+    bool late;
+    if constexpr (VERT) {
+        PV<2> op[Q];
+        late = collide_block<STRICT, 2>(tp, rho, mx, my, obits, omega, op, speed);
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        f2 c[Q];
-        relax_pair<STRICT>(tp[h], rho[h], mx[h], my[h], omega, c);
-        // |u| of the stored values
-        f2 r2, nx_, ny_;
-        moments_pair<STRICT>(c, r2, nx_, ny_);
-        float r0, r1, a0, a1, b0, b1;
-        upk(r2, r0, r1), upk(nx_, a0, a1), upk(ny_, b0, b1);
-        const bool solid0 = (obits >> (2 * h)) & 1u, solid1 = (obits >> (2 * h + 1)) & 1u;
-        late = late & (in_window(r0, a0, b0, 4.76837158203125e-07f /* 2^-21 */, 2097152.f /* 2^21 */, 4.f) | solid0) &
-               (in_window(r1, a1, b1, 4.76837158203125e-07f, 2097152.f, 4.f) | solid1);
-        if constexpr (STRICT) {
-            f2 vx, vy;
-            div2_pair(nx_, ny_, r2, vx, vy);
-            speed_from_sq_pair(add2(mul2_rounded(vx, vx), mul2_rounded(vy, vy)), speed[2 * h], speed[2 * h + 1]);
-        } else {
-            float s0, s1;
-            speed_from_sq_pair(fma2(nx_, nx_, mul2(ny_, ny_)), s0, s1);
-            speed[2 * h] = __fdividef(s0, r0), speed[2 * h + 1] = __fdividef(s1, r1);
-        }
-        // obstacle: bounce-back permutation (speed 0 keeps the streamed value); selected here, per pair, so that the
-        // streamed-in values die early instead of living to the end of the block
-        constexpr int mirror[Q] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+        for (int k = 0; k < Q; k++) upk(op[k].v[0], o[k][0], o[k][1]), upk(op[k].v[1], o[k][2], o[k][3]);
+    } else {
+        late = true;
 #pragma unroll
-        for (int k = 0; k < Q; k++) {
-            float c0, c1;
-            upk(c[k], c0, c1);
-            o[k][2 * h] = solid0 ? t[mirror[k]][2 * h] : c0;
-            o[k][2 * h + 1] = solid1 ? t[mirror[k]][2 * h + 1] : c1;
+        for (int h = 0; h < 2; h++) {
+            PV<1> t1[Q], o1[Q], r1, a1, b1;
+            float sp[2];
+#pragma unroll
+            for (int k = 0; k < Q; k++) t1[k].v[0] = tp[k].v[h];
+            r1.v[0] = rho.v[h], a1.v[0] = mx.v[h], b1.v[0] = my.v[h];
+            late = late & collide_block<STRICT, 1>(t1, r1, a1, b1, (obits >> (2 * h)) & 3u, omega, o1, sp);
+            speed[2 * h] = sp[0], speed[2 * h + 1] = sp[1];
+#pragma unroll
+            for (int k = 0; k < Q; k++) upk(o1[k].v[0], o[k][2 * h], o[k][2 * h + 1]);
         }
     }
-    // ---- the new populations are exact; a |u| whose operands left the late window is redone with the guarded code
+    // the new populations are exact; a |u| whose operands left the late window is redone with the guarded code
     if (!late) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {

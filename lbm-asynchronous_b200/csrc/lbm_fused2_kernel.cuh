@@ -79,13 +79,15 @@ __device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, f
 }
 
 // update4() for this kernel: collide4, the |u| of the four cells straight into one 64-bit total (any split into the
-// two words the host adds up is equivalent), accelerate_flow() at store time on the driven row
+// two words the host adds up is equivalent), accelerate_flow() at store time on the driven row.  Cells whose |u| is
+// not finite (never in a healthy run) are counted straight into shared memory: no register for them.
 template <bool STRICT>
 __device__ __forceinline__ void update4_total(const float (&t)[Q][4], uint32_t obits, bool counted, bool accel, float omega, float w1a,
-                                              float w2a, float (&o)[Q][4], unsigned long long& total, unsigned& nbad)
+                                              float w2a, float (&o)[Q][4], unsigned long long& total, unsigned long long* bad_counter)
 {
     float speed[4];
-    collide4<STRICT>(t, obits, omega, o, speed);
+    collide4<STRICT, false>(t, obits, omega, o, speed);
+    unsigned nbad = 0u;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const bool cnt = counted && !((obits >> j) & 1u);
@@ -93,6 +95,7 @@ __device__ __forceinline__ void update4_total(const float (&t)[Q][4], uint32_t o
         total += (bad || !cnt) ? 0ull : __float2ull_rn(speed[j] * FIX_SCALE);
         nbad += (bad && cnt) ? 1u : 0u;
     }
+    if (nbad) atomicAdd(bad_counter, static_cast<unsigned long long>(nbad));
     if (accel) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -233,7 +236,6 @@ __global__ void __launch_bounds__(32 * R, MINB)
     const size_t pitch = a.pitch;
 
     unsigned long long acc_a = 0ull, acc_b = 0ull;     // per-thread |u| totals (units of 2^-40) of step t1 / t1+1
-    unsigned bad_a = 0u, bad_b = 0u;
     int nbase = 0;                                     // TMA stages consumed by this CTA's earlier units
     bool primed = false;                               // the TMA pipeline has been started
     // request stage number `seq` of this CTA's stage sequence (the current unit starts at sequence number
@@ -287,6 +289,7 @@ __global__ void __launch_bounds__(32 * R, MINB)
         const int le = (a.nx - x0 + 4) >> 2;                 // lane whose first cell is x = nx
         const bool pw0 = west && lane == 0, pw1 = west && lane == 1;
         const bool pe0 = east && lane == le, pe1 = east && lane == le - 1;
+        const bool push_halo = !tma_unit && a.h.on;
 
         for (int c = 0; c < nc; c++) {
             const int q = c * R + warp;                      // this warp's intermediate row, relative to ya-1
@@ -417,10 +420,9 @@ __global__ void __launch_bounds__(32 * R, MINB)
                     const bool accel = (a.accel_row >= 0) && (y == a.accel_row) && (phase == 0 || live2);
                     float o[Q][4];
                     unsigned long long tot = 0ull;
-                    unsigned nbad = 0u;
-                    update4_total<STRICT>(t, obits, counted, accel, a.omega, a.w1a, a.w2a, o, tot, nbad);
-                    if (phase) acc_b += tot, bad_b += nbad;
-                    else acc_a += tot, bad_a += nbad;
+                    update4_total<STRICT>(t, obits, counted, accel, a.omega, a.w1a, a.w2a, o, tot, &s_acc[phase][2]);
+                    if (phase) acc_b += tot;
+                    else acc_a += tot;
 
                     if (phase == 0) {
                         const uint32_t dst = buf2_s + ((q % RB) * F2_B2ROW + 4 * lane) * 4;
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(32 * R, MINB)
 #pragma unroll
                         for (int k = 0; k < Q; k++)
                             *reinterpret_cast<float4*>(dst + k * a.pf) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
-                        if (!tma_unit && a.h.on) {
+                        if (push_halo) {
                             // the rows the neighbour needs for ITS next pair of steps, straight into its ring (peer memory)
                             const bool south = un.kind == 0;
                             const bool near = south ? (y == 0) : (y == a.rows - 1);
@@ -465,19 +467,15 @@ __global__ void __launch_bounds__(32 * R, MINB)
         if (tma_unit) nbase += nst;
     }
 
-    // ---------------- |u| sums of both steps: one reduction per launch ----------------
+    // ---------------- |u| sums of both steps (s_acc[step][0], units of 2^-40) ----------------
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
         acc_a += __shfl_xor_sync(0xffffffffu, acc_a, s);
         acc_b += __shfl_xor_sync(0xffffffffu, acc_b, s);
     }
-    const unsigned nbad_a = __reduce_add_sync(0xffffffffu, bad_a);
-    const unsigned nbad_b = __reduce_add_sync(0xffffffffu, bad_b);
     if (lane == 0) {
         atomicAdd(&s_acc[0][0], acc_a);
         atomicAdd(&s_acc[1][0], acc_b);
-        if (nbad_a) atomicAdd(&s_acc[0][2], static_cast<unsigned long long>(nbad_a));
-        if (nbad_b) atomicAdd(&s_acc[1][2], static_cast<unsigned long long>(nbad_b));
     }
     __syncthreads();
     if (tid < 2) {
