@@ -159,6 +159,7 @@ struct lbm_lattice {
     int loop_resident[2] = {0, 0};
     void (*f2_kernel)(CUtensorMap, CUtensorMap, Fused2Args) = nullptr; // pairs of steps (null: single steps only)
     int f2_r = 0, f2_srows = 0, f2_stages = 0, f2_minb = 0, f2_resident = 0;
+    int f2_iter_rows = 0; // rows a CTA advances per iteration of its marching loop
     size_t f2_smem = 0;
     int prio_high = 0; // numerically lowest = most urgent stream / kernel-node priority of the device
     size_t tma_smem = 0;
@@ -216,9 +217,10 @@ bool tma_by_shape(int ty, int stages, int minb, TmaChoice* c)
     LBM_TMA_CASE(4, 4, 3)
     LBM_TMA_CASE(4, 6, 2)
     LBM_TMA_CASE(16, 2, 1)
-    LBM_TMA_CASE(15, 2, 1)
-    LBM_TMA_CASE(7, 3, 2)
-    LBM_TMA_CASE(7, 4, 2)
+    LBM_TMA_CASE(12, 3, 1)
+    LBM_TMA_CASE(12, 2, 1)
+    LBM_TMA_CASE(10, 4, 1)
+    LBM_TMA_CASE(10, 3, 1)
     LBM_TMA_CASE(16, 3, 1)
 #undef LBM_TMA_CASE
     return false;
@@ -239,22 +241,21 @@ bool f2_by_shape(int r, int srows, int stages, int minb, F2Choice* c)
     }
     LBM_F2_CASE(8, 4, 3, 2)
     LBM_F2_CASE(16, 8, 3, 1)
-    LBM_F2_CASE(16, 4, 6, 1)
     LBM_F2_CASE(12, 4, 4, 1)
 #undef LBM_F2_CASE
     return false;
 }
 
 // opt.kernel:
-//   0            library default.  nx % 4 == 0, nx >= 128, every slab >= 8 rows, halo_lag == 0: step2_kernel, TWO
-//                timesteps per launch (8 consumer warps, stages of 4 rows, 3 stages, 2 CTAs/SM; an odd last step
-//                of a run takes the single-step kernels).  Otherwise single steps: step_tma_kernel (TY 16, 2
-//                stages, 1 CTA/SM) for the interior rows when nx % 4 == 0, nx >= 128 and the slab has >= 3 rows,
-//                step_vec4_kernel / step_scalar_kernel for the rest
+//   0            library default.  Single steps: step_tma_kernel (strict: 10-row tiles, 4 stages, 1 CTA/SM; fast: 8-row
+//                tiles) for the interior rows when nx % 4 == 0, nx >= 128 and the slab has >= 3 rows,
+//                step_vec4_kernel / step_scalar_kernel for the rest.  Fast flavour with nx % 4 == 0, nx >= 128, every
+//                slab >= 8 rows, halo_lag == 0: step2_kernel, TWO timesteps per launch (8 warps, stages of 4 rows, 3
+//                stages, 2 CTAs/SM; an odd last step of a run takes the single-step kernels)
 //   2RRSNM       step2_kernel with RR warps (rows per iteration), S rows per stage, N stages, M CTAs per SM asked of
-//                the compiler (208432 216831 216461 212441)
+//                the compiler (208432 216831 212441)
 //   1TTSM        step_tma_kernel with TT rows per tile, S stages, M resident CTAs per SM asked of the compiler
-//                (10823 10822 10832 10831 10841 10434 10444 10443 10462 11621 11631)
+//                (10823 10822 10832 10831 10841 10434 10444 10443 10462 11621 11631 11231 11221 11041 11031)
 //   H M (10..39) step_vec4_kernel for every row: hint = H-1 (0 plain, 1 ld.nc.no_allocate, 2 + st.cs), min blocks M
 //   99           step_scalar_kernel for every row
 //   200          step_loop_kernel (all steps of a run in one cooperative launch); also the default for
@@ -281,16 +282,21 @@ KernelChoice choose_kernel(const lbm_options_t& o, int nx)
     k.minb = 1;
     k.block = (o.block == 128 || o.block == 256 || o.block == 512) ? o.block : 256;
     k.tma = k.vec4 && nx >= TMA_TX && (o.kernel == 0 || (o.kernel >= 200 && o.kernel <= 204) || o.kernel >= 10000);
-    // best of the r01 sweeps (profiles/r01_variant_sweep.md): the strict flavour is instruction heavy and wants
-    // many consumer warps (16 rows x 2 stages), the fast flavour is load-latency bound and wants a deeper pipeline
-    // of smaller tiles (8 rows x 4 stages)
+    // best of the sweeps (profiles/r02_kernel_sweep.md).  With the packed collision both flavours want few, fat warps:
+    // the strict flavour 10 consumer warps with ~124 registers each (both pairs of a thread side by side through the
+    // collision) and a 4-stage pipeline of 10-row tiles -- 92 GLUPS at 8192^2, HBM bound; the fast flavour the 8-row
+    // tiles of round 1
     if (o.arith == LBM_ARITH_FAST)
         k.tma_ty = 8, k.tma_stages = 4, k.tma_minb = 1;
     else
-        k.tma_ty = 16, k.tma_stages = 2, k.tma_minb = 1;
-    // pairs of steps: default wherever the TMA path applies; an explicit single-step variant (1TTSM, H M, 99)
-    // or a deterministic halo lag (defined per single step) switches it off
-    k.f2 = k.tma && (o.kernel == 0 || (o.kernel >= 200 && o.kernel <= 204) || o.kernel >= 200000) && o.halo_lag == 0;
+        k.tma_ty = 10, k.tma_stages = 4, k.tma_minb = 1;
+    // pairs of steps (step2_kernel): half the HBM traffic, but bound by the latency of the collision's dependency
+    // chains at 16 warps of 128 registers per SM.  Default for the fast flavour (93-96 GLUPS against 90 from single
+    // steps); the strict flavour is faster on single steps (92 against 83-85), where it reaches the HBM roofline.
+    // An explicit 2RRSNM code selects it for either; an explicit single-step variant (1TTSM, H M, 99) or a
+    // deterministic halo lag (defined per single step) switches it off
+    const bool f2_default = (o.kernel == 0 || (o.kernel >= 200 && o.kernel <= 204)) && o.arith == LBM_ARITH_FAST;
+    k.f2 = k.tma && (f2_default || o.kernel >= 200000) && o.halo_lag == 0;
     k.f2_r = 8, k.f2_srows = 4, k.f2_stages = 3, k.f2_minb = 2;
     if (o.kernel >= 200000) {
         k.f2_r = (o.kernel - 200000) / 1000;
@@ -441,7 +447,7 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
                 const int h = (interior + nseg - 1) / nseg;
                 const long long units = static_cast<long long>((interior + h - 1) / h) * s.f2_nsx;
                 const long long waves = (units + g_max - 1) / g_max;
-                const int iters = (h + 2 + L->f2_r - 1) / L->f2_r;
+                const int iters = (h + 2 + L->f2_iter_rows - 1) / L->f2_iter_rows;
                 const double cost = static_cast<double>(waves) * (iters + 0.5);
                 if (cost < best_cost - 1e-9) best_cost = cost, best_nseg = nseg;
             }
@@ -986,6 +992,7 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
                         k.f2_srows, k.f2_stages, k.f2_minb);
         L->f2_kernel = c.fn;
         L->f2_r = c.r, L->f2_srows = c.srows, L->f2_stages = c.stages, L->f2_minb = c.minb;
+        L->f2_iter_rows = c.r;
         L->f2_smem = (static_cast<size_t>(c.stages) * stage_floats(c.srows) + static_cast<size_t>(c.r + 2) * F2_B2ROW) * sizeof(float) + 64;
         for (int i = 0; i < L->nslabs; i++) {
             CU(cudaSetDevice(L->slabs[i].device));

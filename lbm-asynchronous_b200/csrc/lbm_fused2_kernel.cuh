@@ -179,6 +179,31 @@ __device__ __forceinline__ F2Unit f2_unit(const Fused2Args& a, int u)
     return r;
 }
 
+// boundary units of a slab with neighbours: the four cells just stored (row y of the slab's first / last two rows) go
+// straight into the ring of the neighbour that needs them for ITS next pair of steps (peer memory over NVLink)
+__device__ __forceinline__ void f2_push_rows(const Fused2Args& a, bool south, int y, int xg, int epoch, const float (&o)[Q][4])
+{
+    const size_t pitch = a.pitch;
+    const bool near = south ? (y == 0) : (y == a.rows - 1);
+    float* ring = (south ? a.h.hs.send_ring : a.h.hn.send_ring) + static_cast<size_t>(ring_slot(epoch + 1, a.h.ring)) * a.h.slot_stride + xg;
+    // planes crossing towards the neighbour: 4,7,8 southwards, 2,5,6 northwards
+    const float4 ca = south ? make_float4(o[4][0], o[4][1], o[4][2], o[4][3]) : make_float4(o[2][0], o[2][1], o[2][2], o[2][3]);
+    const float4 cb = south ? make_float4(o[7][0], o[7][1], o[7][2], o[7][3]) : make_float4(o[5][0], o[5][1], o[5][2], o[5][3]);
+    const float4 cc = south ? make_float4(o[8][0], o[8][1], o[8][2], o[8][3]) : make_float4(o[6][0], o[6][1], o[6][2], o[6][3]);
+    if (near) {
+        *reinterpret_cast<float4*>(ring + 0 * pitch) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
+        *reinterpret_cast<float4*>(ring + 1 * pitch) = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
+        *reinterpret_cast<float4*>(ring + 2 * pitch) = make_float4(o[3][0], o[3][1], o[3][2], o[3][3]);
+        *reinterpret_cast<float4*>(ring + 3 * pitch) = ca;
+        *reinterpret_cast<float4*>(ring + 4 * pitch) = cb;
+        *reinterpret_cast<float4*>(ring + 5 * pitch) = cc;
+    } else {
+        *reinterpret_cast<float4*>(ring + 6 * pitch) = ca;
+        *reinterpret_cast<float4*>(ring + 7 * pitch) = cb;
+        *reinterpret_cast<float4*>(ring + 8 * pitch) = cc;
+    }
+}
+
 // dispatch f2_load_plane_generic on a run-time plane index
 template <int SROWS>
 __device__ __forceinline__ void f2_load_plane_any(int k, const Fused2Args& a, float* stage, int x0, int ya, int epoch, int lane)
@@ -433,29 +458,7 @@ __global__ void __launch_bounds__(32 * R, MINB)
 #pragma unroll
                         for (int k = 0; k < Q; k++)
                             *reinterpret_cast<float4*>(dst + k * a.pf) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
-                        if (push_halo) {
-                            // the rows the neighbour needs for ITS next pair of steps, straight into its ring (peer memory)
-                            const bool south = un.kind == 0;
-                            const bool near = south ? (y == 0) : (y == a.rows - 1);
-                            float* ring = (south ? a.h.hs.send_ring : a.h.hn.send_ring) +
-                                          static_cast<size_t>(ring_slot(epoch + 1, a.h.ring)) * a.h.slot_stride + xg;
-                            // planes crossing towards the neighbour: 4,7,8 southwards, 2,5,6 northwards
-                            const float4 ca = south ? make_float4(o[4][0], o[4][1], o[4][2], o[4][3]) : make_float4(o[2][0], o[2][1], o[2][2], o[2][3]);
-                            const float4 cb = south ? make_float4(o[7][0], o[7][1], o[7][2], o[7][3]) : make_float4(o[5][0], o[5][1], o[5][2], o[5][3]);
-                            const float4 cc = south ? make_float4(o[8][0], o[8][1], o[8][2], o[8][3]) : make_float4(o[6][0], o[6][1], o[6][2], o[6][3]);
-                            if (near) {
-                                *reinterpret_cast<float4*>(ring + 0 * pitch) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
-                                *reinterpret_cast<float4*>(ring + 1 * pitch) = make_float4(o[1][0], o[1][1], o[1][2], o[1][3]);
-                                *reinterpret_cast<float4*>(ring + 2 * pitch) = make_float4(o[3][0], o[3][1], o[3][2], o[3][3]);
-                                *reinterpret_cast<float4*>(ring + 3 * pitch) = ca;
-                                *reinterpret_cast<float4*>(ring + 4 * pitch) = cb;
-                                *reinterpret_cast<float4*>(ring + 5 * pitch) = cc;
-                            } else {
-                                *reinterpret_cast<float4*>(ring + 6 * pitch) = ca;
-                                *reinterpret_cast<float4*>(ring + 7 * pitch) = cb;
-                                *reinterpret_cast<float4*>(ring + 8 * pitch) = cc;
-                            }
-                        }
+                        if (push_halo) f2_push_rows(a, un.kind == 0, y, xg, epoch, o);
                     }
                 }
                 // phase 0 -> 1: the ring rows are complete and every warp holds its staged row in registers;

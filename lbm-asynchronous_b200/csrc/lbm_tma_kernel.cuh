@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(32 * TY + 32, MINB)
             }
             float o[Q][4];
             SpeedAcc acc = {0u, 0u, 0u}; // this tile's four cells: lo < 2^26, hi < 2^20
-            update4<STRICT, (MINB == 1 && TY <= 8)>(t, obits, valid, accel_live && (y == a.accel_row), a.omega, a.w1a, a.w2a, o, acc);
+            update4<STRICT, (MINB == 1 && TY <= 12)>(t, obits, valid, accel_live && (y == a.accel_row), a.omega, a.w1a, a.w2a, o, acc);
             acc_lo += acc.lo, acc_hi += acc.hi, acc_bad += acc.bad;
 
             if (valid) {

@@ -78,6 +78,7 @@ def exact_tot_u(orc, p, obst, cells_before, k):
     # step_tma_kernel for the interior rows (TY rows per tile, stages): full, partial and single tiles
     (128, 128, 10832, 0), (128, 3, 10832, 0), (128, 4, 10823, 0), (256, 37, 10841, 0), (384, 20, 10443, 0),
     (132, 11, 10462, 0), (1024, 9, 11621, 0), (640, 40, 11631, 0), (2052, 7, 10822, 0), (4096, 70, 10434, 128),
+    (256, 45, 11041, 0), (1024, 23, 11031, 0), (640, 300, 11231, 0), (2052, 130, 11221, 0), (4096, 333, 11041, 0),
     (128, 64, 32, 256),                                                     # step_vec4_kernel for every row
     (256, 37, 200, 128), (1024, 700, 200, 0), (4096, 200, 204, 256), (12, 9, 200, 0),  # step_loop_kernel (cooperative)
     (127, 33, 201, 0), (640, 300, 201, 0), (1, 5, 200, 0), (64, 64, 204, 0),
