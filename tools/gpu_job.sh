@@ -1,5 +1,6 @@
 #!/bin/bash
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/f2_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/f2_pytest.log
-tail -n 4 gpurun_out/f2_pytest.log
-timeout 200 python bench.py --arith fast --no-cpu-baseline > gpurun_out/f2_bench_n1_fast.json 2> gpurun_out/f2_bench_n1_fast.err; echo "bench fast rc=$?"
-timeout 20 python tools/bench_line.py gpurun_out/f2_bench_n1_fast.json < /dev/null
+timeout 400 python -m pytest tests/test_gpu_multi.py -m gpu -q > gpurun_out/r02b_gputest_multi.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/r02b_gputest_multi.txt
+tail -n 3 gpurun_out/r02b_gputest_multi.txt
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 10 > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err; echo "bench rc=$?"
+timeout 20 python tools/bench_line.py gpurun_out/r02_bench_n2.json < /dev/null
+tail -n 3 gpurun_out/r02_bench_n2.err
