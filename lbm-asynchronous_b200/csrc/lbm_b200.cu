@@ -17,6 +17,8 @@
 #include "lbm_kernels.cuh"
 #include "lbm_tma_kernel.cuh"
 #include "lbm_fused2_kernel.cuh"
+#include "lbm_cluster_kernel.cuh"
+#include "lbm_ll_kernel.cuh"
 
 #include <cudaTypedefs.h>
 #include <unistd.h>
@@ -116,6 +118,15 @@ struct Slab {
     unsigned loop_grid = 0;
     int loop_vec = 4, loop_block = 256, loop_tw_shift = 0, loop_nbx = 0, loop_nby = 0, loop_nxv = 0, loop_ntiles = 0;
     unsigned* loop_barrier = nullptr;
+    // whole runs in one launch of step_cluster_kernel: the lattice lives in the shared memory of one cluster
+    bool use_cluster = false;
+    int cl_size = 0, cl_rpc = 0, cl_threads = 0;
+    size_t cl_smem = 0;
+    // whole runs in one cooperative launch of step_ll_kernel: a row per CTA, cells in registers, packets through L2
+    bool use_ll = false;
+    int ll_block = 0;
+    size_t ll_smem = 0;
+    uint4* ll_packets = nullptr; // [2 directions][2 parities][rows][pitch]
     // interior rows through step_tma_kernel
     bool use_tma = false;
     CUtensorMap tmap[2];  // per lattice: boxes TMA_TX wide
@@ -157,6 +168,11 @@ struct lbm_lattice {
     void (*tma_kernel)(CUtensorMap, CUtensorMap, TmaArgs) = nullptr; // interior rows (null: `kernel` does every row)
     int tma_ty = 0, tma_stages = 0, tma_minb = 0, tma_resident = 0, sm_count = 0;
     int loop_resident[2] = {0, 0};
+    void (*ll_kernel)(LLArgs) = nullptr;           // step_ll_kernel (null: not available for this lattice)
+    unsigned ll_flags = 0;                         // packet flags handed out so far (never reused)
+    void (*cluster_kernel)(ClusterArgs) = nullptr; // step_cluster_kernel (null: not available for this lattice)
+    int cl_cpt = 0, cl_vert = 0, cl_maxt = 0;      // its cells per thread, collision shape, thread limit
+    int cl_sync = 0;                               // barrier fencing (tuning knob LBM_CL_SYNC)
     void (*f2_kernel)(CUtensorMap, CUtensorMap, Fused2Args) = nullptr; // pairs of steps (null: single steps only)
     int f2_r = 0, f2_srows = 0, f2_stages = 0, f2_minb = 0, f2_resident = 0;
     int f2_iter_rows = 0; // rows a CTA advances per iteration of its marching loop
@@ -246,6 +262,29 @@ bool f2_by_shape(int r, int srows, int stages, int minb, F2Choice* c)
     return false;
 }
 
+struct ClusterChoice {
+    int cpt, vert, maxt;
+    void (*fn)(ClusterArgs);
+};
+template <bool STRICT>
+bool cluster_by_shape(int cpt, int vert, int maxt, ClusterChoice* c)
+{
+#define LBM_CL_CASE(C_, V_, T_)                                                      \
+    if (cpt == C_ && vert == V_ && maxt == T_) {                                     \
+        *c = {C_, V_, T_, step_cluster_kernel<STRICT, C_, (V_ != 0), T_>};           \
+        return true;                                                                 \
+    }
+    LBM_CL_CASE(4, 1, 256)
+    LBM_CL_CASE(4, 0, 256)
+    LBM_CL_CASE(4, 0, 512)
+    LBM_CL_CASE(4, 0, 1024)
+    LBM_CL_CASE(2, 0, 512)
+    LBM_CL_CASE(2, 0, 1024)
+    LBM_CL_CASE(1, 0, 1024)
+#undef LBM_CL_CASE
+    return false;
+}
+
 // opt.kernel:
 //   0            library default.  Single steps: step_tma_kernel (strict: 10-row tiles, 4 stages, 1 CTA/SM; fast: 8-row
 //                tiles) for the interior rows when nx % 4 == 0, nx >= 128 and the slab has >= 3 rows,
@@ -261,10 +300,24 @@ bool f2_by_shape(int r, int srows, int stages, int minb, F2Choice* c)
 //   200          step_loop_kernel (all steps of a run in one cooperative launch); also the default for
 //                single-slab grids whose two lattices fit in L2 (<= LOOP_MAX_CELLS cells).  201 / 204 force
 //                its 1-cell / 4-cell per thread mapping (default: 1 cell up to LOOP_VEC4_CELLS cells per slab)
+//   3000         step_cluster_kernel (all steps of a run in one launch, the lattice resident in the shared memory of one
+//                cluster of up to 16 CTAs); also the default for single-slab grids of up to CLUSTER_MAX_CELLS cells.
+//                3CVM forces C cells per thread (1, 2, 4), V = 1 both pairs of a thread side by side through the
+//                collision, M x 256 threads per CTA at most (3411 3401 3402 3404 3202 3204 3104)
+//   400          step_ll_kernel (all steps of a run in one cooperative launch, a row per CTA, cells in registers, rows
+//                exchanging flagged 16-byte packets through L2); also the default for single-slab grids of up to
+//                LL_MAX_CELLS cells with nx <= 1024 whose rows are all resident at once
+constexpr long long LL_MAX_CELLS = 70000; // up to 256 x 256
+constexpr int LL_SLOTS = 8;               // slots of the per-step sums (one RED per CTA, step and word)
+constexpr long long CLUSTER_MAX_CELLS = 32768; // 128 x 256: above, 16 SMs have more arithmetic than the whole GPU has latency
+constexpr int CLUSTER_MAX_CTAS = 16;
 constexpr long long LOOP_MAX_CELLS = 1400000; // 2 x 36 B x cells <= ~100 MB of the 126 MB L2
 constexpr long long LOOP_VEC4_CELLS = 70000;  // up to 256 x 256: one cell per thread (<= 512 CTAs of 128 threads) beats four;
                                               // above, the one-counter grid barrier gets too slow for that many CTAs
 struct KernelChoice {
+    bool ll;
+    bool cluster;
+    int cl_cpt, cl_vert, cl_maxt; // 0: chosen from the grid's shape
     bool loop;
     bool vec4;
     int hint, block, minb;
@@ -277,11 +330,16 @@ KernelChoice choose_kernel(const lbm_options_t& o, int nx)
 {
     KernelChoice k;
     k.vec4 = (nx % 4 == 0) && o.kernel != 99;
-    k.loop = (o.kernel == 0 || o.kernel == 200 || o.kernel == 201 || o.kernel == 204);
+    const bool cl_code = (o.kernel >= 3000 && o.kernel < 4000) || o.kernel == 400; // everything else as the default
+    k.ll = (o.kernel == 0 || o.kernel == 400);
+    k.cluster = (o.kernel >= 3000 && o.kernel < 4000); // not a default: step_ll_kernel is faster wherever both apply
+    k.cl_cpt = k.cl_vert = k.cl_maxt = 0;
+    if (k.cluster && o.kernel != 3000) k.cl_cpt = (o.kernel / 100) % 10, k.cl_vert = (o.kernel / 10) % 10, k.cl_maxt = 256 * (o.kernel % 10);
+    k.loop = (o.kernel == 0 || cl_code || o.kernel == 200 || o.kernel == 201 || o.kernel == 204);
     k.hint = 0;
     k.minb = 1;
     k.block = (o.block == 128 || o.block == 256 || o.block == 512) ? o.block : 256;
-    k.tma = k.vec4 && nx >= TMA_TX && (o.kernel == 0 || (o.kernel >= 200 && o.kernel <= 204) || o.kernel >= 10000);
+    k.tma = k.vec4 && nx >= TMA_TX && (o.kernel == 0 || cl_code || (o.kernel >= 200 && o.kernel <= 204) || o.kernel >= 10000);
     // best of the sweeps (profiles/r02_kernel_sweep.md).  With the packed collision both flavours want few, fat warps:
     // the strict flavour 10 consumer warps with ~124 registers each (both pairs of a thread side by side through the
     // collision) and a 4-stage pipeline of 10-row tiles -- 92 GLUPS at 8192^2, HBM bound; the fast flavour the 8-row
@@ -295,7 +353,7 @@ KernelChoice choose_kernel(const lbm_options_t& o, int nx)
     // steps); the strict flavour is faster on single steps (92 against 83-85), where it reaches the HBM roofline.
     // An explicit 2RRSNM code selects it for either; an explicit single-step variant (1TTSM, H M, 99) or a
     // deterministic halo lag (defined per single step) switches it off
-    const bool f2_default = (o.kernel == 0 || (o.kernel >= 200 && o.kernel <= 204)) && o.arith == LBM_ARITH_FAST;
+    const bool f2_default = (o.kernel == 0 || cl_code || (o.kernel >= 200 && o.kernel <= 204)) && o.arith == LBM_ARITH_FAST;
     k.f2 = k.tma && (f2_default || o.kernel >= 200000) && o.halo_lag == 0;
     k.f2_r = 8, k.f2_srows = 4, k.f2_stages = 3, k.f2_minb = 2;
     if (o.kernel >= 200000) {
@@ -384,7 +442,7 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
     // default: single slab only -- across GPUs the resident kernels measured no better than the graph path
     // (profiles/r01_small_grids.md); kernel codes 200/201/204 ask for it explicitly
     if (k.loop && L->opt.use_graph && !L->interleaved &&
-        (L->opt.kernel >= 200 || (total_slabs == 1 && nominal_cells <= LOOP_MAX_CELLS))) {
+        ((L->opt.kernel >= 200 && L->opt.kernel <= 204) || (total_slabs == 1 && nominal_cells <= LOOP_MAX_CELLS))) {
         bool v4 = k.vec4 && nominal_cells >= LOOP_VEC4_CELLS;
         if (L->opt.kernel == 201) v4 = false;
         if (L->opt.kernel == 204) v4 = k.vec4;
@@ -407,6 +465,25 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
             s.use_loop = true;
         }
     }
+    // the lattice resident in one cluster's shared memory: single slab, the shape fixed in common_setup()
+    s.use_cluster = false;
+    if (k.cluster && L->cluster_kernel && L->opt.use_graph && !L->interleaved && total_slabs == 1 && L->nslabs == 1 && s.cl_size > 0)
+        s.use_cluster = true;
+    // a row per CTA, all rows resident (cooperative launch)
+    s.use_ll = false;
+    if (k.ll && L->ll_kernel && L->opt.use_graph && !L->interleaved && total_slabs == 1 && L->nslabs == 1 && L->p.nx <= 1024 &&
+        (L->opt.kernel == 400 || nominal_cells <= LL_MAX_CELLS)) {
+        const int block = (L->p.nx + 31) / 32 * 32;
+        const size_t smem = (2 * 6 * static_cast<size_t>(block) + 2 * (block / 32) * 4) * sizeof(float);
+        int resident = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, reinterpret_cast<const void*>(L->ll_kernel), block, smem) == cudaSuccess &&
+            static_cast<long long>(resident) * L->sm_count >= s.rows) {
+            s.use_ll = true;
+            s.ll_block = block, s.ll_smem = smem;
+        }
+        cudaGetLastError();
+    }
+    if (L->opt.kernel == 400 && !s.use_ll && getenv("LBM_DEBUG")) fprintf(stderr, "[lbm] step_ll_kernel asked for but not applicable\n");
     s.use_tma = !s.use_loop && k.tma && L->tma_kernel && s.rows >= 3;
     if (s.use_tma) {
         const int interior = s.rows - 2;
@@ -476,6 +553,7 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
     int slots = 1;
     while (slots < 64 && static_cast<unsigned>(slots) * 1024u < ctas) slots <<= 1;
     s.nslots = slots;
+    if (s.use_ll) s.nslots = LL_SLOTS; // one RED per CTA, step and word: spread them
 }
 
 // the lattice as a 3-D tensor (x, y, plane) for the TMA unit; boxes are (TMA_TX | TMA_TXW) x box_rows x 1
@@ -959,6 +1037,78 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
             if (!coop) L->loop_kernel[v] = nullptr;
         }
     }
+    if (k.ll && !L->interleaved && !uses_halo_cfg(L) && L->nslabs == 1) {
+        CU(cudaSetDevice(L->slabs[0].device));
+        int sms = 0, coop = 0;
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, L->slabs[0].device));
+        CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, L->slabs[0].device));
+        L->sm_count = sms;
+        if (coop) {
+            L->ll_kernel = strict ? step_ll_kernel<true> : step_ll_kernel<false>;
+            CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(L->ll_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        }
+    }
+    if (k.cluster && !L->interleaved && !uses_halo_cfg(L) && L->nslabs == 1) {
+        // one cluster of C CTAs (a power of two <= 16 and <= rows), rows dealt out in blocks of rpc = ceil(rows / C)
+        Slab& s0 = L->slabs[0];
+        const int rows = params->ny, nx = params->nx;
+        const long long cells = static_cast<long long>(nx) * rows;
+        const bool asked = (L->opt.kernel >= 3000 && L->opt.kernel < 4000);
+        CU(cudaSetDevice(s0.device));
+        int cl_ok = 0;
+        CU(cudaDeviceGetAttribute(&cl_ok, cudaDevAttrClusterLaunch, s0.device));
+        for (int C = CLUSTER_MAX_CTAS; cl_ok && C >= 1 && !L->cluster_kernel && (asked || cells <= CLUSTER_MAX_CELLS); C >>= 1) {
+            if (C > rows) continue;
+            const int rpc = (rows + C - 1) / C;
+            int cpt = k.cl_cpt, vert = k.cl_vert, maxt = k.cl_maxt;
+            if (cpt == 0) {
+                // few fat threads: four cells per thread whenever the row length allows it
+                cpt = (nx % 4 == 0) ? 4 : ((nx % 2 == 0) ? 2 : 1);
+                const long long t = static_cast<long long>(rpc) * (nx / cpt);
+                if (cpt == 4) maxt = (t <= 256) ? 256 : ((t <= 512) ? 512 : 1024), vert = (maxt == 256);
+                else if (cpt == 2) maxt = (t <= 512) ? 512 : 1024, vert = 0;
+                else maxt = 1024, vert = 0;
+            }
+            if (cpt < 1 || nx % cpt) {
+                if (asked && k.cl_cpt) return fail(LBM_EINVAL, "step_cluster_kernel: nx = %d is not a multiple of %d cells per thread", nx, cpt);
+                break;
+            }
+            const long long threads = static_cast<long long>(rpc) * (nx / cpt);
+            const size_t smem = 2 * static_cast<size_t>(Q) * rpc * nx * sizeof(float); // two copies
+            if (threads > maxt || smem > 220 * 1024) {
+                if (C == CLUSTER_MAX_CTAS && asked)
+                    return fail(LBM_EINVAL, "step_cluster_kernel: %d x %d does not fit (%lld threads per CTA of %d allowed, %zu B of shared memory)",
+                                nx, rows, threads, maxt, smem);
+                break; // fewer CTAs only make it worse
+            }
+            ClusterChoice c;
+            const bool ok = strict ? cluster_by_shape<true>(cpt, vert, maxt, &c) : cluster_by_shape<false>(cpt, vert, maxt, &c);
+            if (!ok) return fail(LBM_EINVAL, "no step_cluster_kernel variant with %d cells per thread, vert %d, %d threads", cpt, vert, maxt);
+            const void* fn = reinterpret_cast<const void*>(c.fn);
+            CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            if (C > 8) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = static_cast<unsigned>(C), at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+            cfg.gridDim = dim3(C), cfg.blockDim = dim3(static_cast<unsigned>((threads + 31) / 32 * 32));
+            cfg.dynamicSmemBytes = smem, cfg.attrs = at, cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters < 1) {
+                cudaGetLastError();
+                continue; // this device does not co-schedule that many CTAs of this size: try half
+            }
+            L->cluster_kernel = c.fn;
+            L->cl_cpt = cpt, L->cl_vert = vert, L->cl_maxt = maxt;
+            s0.cl_size = C, s0.cl_rpc = rpc, s0.cl_threads = static_cast<int>(cfg.blockDim.x), s0.cl_smem = smem;
+        }
+        if (asked && !L->cluster_kernel) return fail(LBM_ECUDA, "step_cluster_kernel cannot be launched on this device");
+        if (const char* t = getenv("LBM_CL_SYNC")) L->cl_sync = atoi(t);
+        if (getenv("LBM_DEBUG") && L->cluster_kernel)
+            fprintf(stderr, "[lbm] step_cluster_kernel: %d CTAs x %d threads, %d rows per CTA, %d cells per thread (vert %d, <= %d threads), %zu B smem\n",
+                    s0.cl_size, s0.cl_threads, s0.cl_rpc, L->cl_cpt, L->cl_vert, L->cl_maxt, s0.cl_smem);
+    }
     if (k.tma) {
         TmaChoice c;
         const bool ok = strict ? tma_by_shape<true>(k.tma_ty, k.tma_stages, k.tma_minb, &c)
@@ -1026,6 +1176,7 @@ void free_slab(Slab& s)
     cudaFree(s.sums_ref);
     cudaFree(s.state_sums);
     cudaFree(s.loop_barrier);
+    cudaFree(s.ll_packets);
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
@@ -1460,7 +1611,24 @@ int lbm_run(lbm_lattice_t* L, int iters)
     const int parity = L->cur;
     const bool use_graphs = L->opt.use_graph && !L->interleaved;
     bool all_loop = true, f2 = true;
+    const bool ll = (L->nslabs == 1 && L->slabs[0].use_ll);
+    const bool cluster = !ll && (L->nslabs == 1 && L->slabs[0].use_cluster);
     for (int i = 0; i < L->nslabs; i++) all_loop = all_loop && L->slabs[i].use_loop, f2 = f2 && L->slabs[i].use_f2;
+    if (cluster || ll) all_loop = true; // no graphs, no per-step launches
+    if (ll) {
+        // packet buffers (zeroed: flag 0 is never waited for); flags are never reused by a lattice
+        Slab& s = L->slabs[0];
+        CU(cudaSetDevice(s.device));
+        const size_t bytes = 4 * static_cast<size_t>(s.rows) * L->pitch * sizeof(uint4);
+        if (!s.ll_packets) {
+            CU(cudaMalloc(&s.ll_packets, bytes));
+            CU(cudaMemsetAsync(s.ll_packets, 0, bytes, s.stream));
+            L->ll_flags = 0;
+        } else if (static_cast<unsigned long long>(L->ll_flags) + static_cast<unsigned long long>(iters) + 1ull > 0xffffffffull) {
+            CU(cudaMemsetAsync(s.ll_packets, 0, bytes, s.stream));
+            L->ll_flags = 0;
+        }
+    }
     // everything that can fail without having touched the lattice comes first: a failure here leaves the run
     // un-started and the call can be repeated
     for (int i = 0; i < L->nslabs; i++) {
@@ -1531,7 +1699,67 @@ int lbm_run(lbm_lattice_t* L, int iters)
     int done = 0;        // timesteps queued
     long long passes = 0; // lattice swaps queued
     long long epochs = 0; // halo epochs queued after epoch_base
-    if (all_loop) {
+    if (ll) {
+        // every step of this run in ONE cooperative launch of step_ll_kernel, a CTA per row
+        Slab& s = L->slabs[0];
+        CU(cudaSetDevice(s.device));
+        LLArgs a;
+        memset(&a, 0, sizeof a);
+        a.lat[0] = s.lat[0], a.lat[1] = s.lat[1];
+        a.pf = plane_floats(L, s);
+        a.obst = s.obst;
+        a.sums = s.sums;
+        a.nslots = s.nslots;
+        const size_t half = 2 * static_cast<size_t>(s.rows) * L->pitch;
+        a.pk_north = s.ll_packets, a.pk_south = s.ll_packets + half;
+        a.flag_base = L->ll_flags;
+        a.error = s.error;
+        a.timeout_ns = L->timeout_ns;
+        a.first_step = first, a.nsteps = iters, a.last_step = first + iters - 1;
+        a.src = parity;
+        a.nx = L->p.nx, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
+        a.accel_row = s.accel_row;
+        a.omega = L->p.omega, a.w1a = L->w1a, a.w2a = L->w2a;
+        void* kp[1] = {&a};
+        CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(L->ll_kernel), dim3(static_cast<unsigned>(s.rows)),
+                                       dim3(static_cast<unsigned>(s.ll_block)), kp, s.ll_smem, s.stream));
+        L->ll_flags += static_cast<unsigned>(iters);
+        L->launches++;
+        done = iters;
+        passes = iters;
+        epochs = iters;
+    } else if (cluster) {
+        // every step of this run in ONE launch of step_cluster_kernel: the lattice goes to the cluster's shared
+        // memory, comes back after the last step
+        Slab& s = L->slabs[0];
+        CU(cudaSetDevice(s.device));
+        ClusterArgs a;
+        memset(&a, 0, sizeof a);
+        a.lat[0] = s.lat[0], a.lat[1] = s.lat[1];
+        a.pf = plane_floats(L, s);
+        a.obst = s.obst;
+        a.sums = s.sums;
+        a.nslots = s.nslots;
+        a.first_step = first, a.nsteps = iters, a.last_step = first + iters - 1;
+        a.src = parity;
+        a.nx = L->p.nx, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
+        a.rpc = s.cl_rpc;
+        a.accel_row = s.accel_row;
+        a.sync_mode = L->cl_sync;
+        a.omega = L->p.omega, a.w1a = L->w1a, a.w2a = L->w2a;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = static_cast<unsigned>(s.cl_size), at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3(static_cast<unsigned>(s.cl_size)), cfg.blockDim = dim3(static_cast<unsigned>(s.cl_threads));
+        cfg.dynamicSmemBytes = s.cl_smem, cfg.stream = s.stream, cfg.attrs = at, cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, L->cluster_kernel, a));
+        L->launches++;
+        done = iters;
+        passes = iters;
+        epochs = iters;
+    } else if (all_loop) {
         // every step of this run in cooperative launches of step_loop_kernel, one per slab (slabs on different
         // GPUs run at the same time and exchange halo rows and flags); more than one launch per slab only if
         // the 32-bit barrier counter would overflow

@@ -82,6 +82,18 @@ def exact_tot_u(orc, p, obst, cells_before, k):
     (128, 64, 32, 256),                                                     # step_vec4_kernel for every row
     (256, 37, 200, 128), (1024, 700, 200, 0), (4096, 200, 204, 256), (12, 9, 200, 0),  # step_loop_kernel (cooperative)
     (127, 33, 201, 0), (640, 300, 201, 0), (1, 5, 200, 0), (64, 64, 204, 0),
+    # step_cluster_kernel (lattice resident in one cluster's shared memory): 3000 = shape chosen by the library,
+    # 3CVM = C cells per thread, V both pairs side by side, M x 256 threads; ragged row blocks, CTAs without rows,
+    # fewer rows than CTAs, rows shorter than a warp
+    (128, 128, 3000, 0), (128, 128, 3401, 0), (128, 128, 3202, 0), (128, 128, 3104, 0), (128, 64, 3411, 0),
+    (256, 37, 3402, 0), (64, 50, 3202, 0), (127, 20, 3104, 0), (100, 30, 3000, 0), (32, 33, 3000, 0), (8, 12, 3000, 0),
+    (4, 5, 3000, 0), (1, 8, 3000, 0), (3, 3, 3000, 0), (130, 2, 3000, 0), (36, 21, 3401, 0), (128, 256, 3000, 0),
+    (256, 128, 3404, 0), (256, 128, 3204, 0), (512, 16, 3000, 0), (1024, 7, 3000, 0),
+    # step_ll_kernel (a row per CTA, cells in registers, flagged packets between rows): partial warps, one-row and
+    # one-column grids, the widest row a CTA takes
+    (128, 128, 400, 0), (128, 256, 400, 0), (256, 256, 400, 0), (64, 50, 400, 0), (127, 20, 400, 0), (100, 30, 400, 0),
+    (32, 33, 400, 0), (8, 12, 400, 0), (4, 5, 400, 0), (1, 8, 400, 0), (3, 3, 400, 0), (130, 2, 400, 0), (5, 2, 400, 0),
+    (1024, 9, 400, 0), (1000, 2, 400, 0), (333, 290, 400, 0),
 ])
 def test_strict_steps_bit_exact_vs_oracle(gpu, pkg, orc, nx, ny, kernel, block):
     p, obst, cells0 = random_case(orc, nx, ny, seed=nx * 1000 + ny)
@@ -155,7 +167,8 @@ def test_av_vels_identical_across_kernel_variants(gpu, pkg, orc):
     same sums bit for bit."""
     p, obst, cells0 = random_case(orc, 256, 40, seed=7)
     ref = None
-    for kernel, block in [(0, 0), (10, 128), (21, 512), (99, 0), (99, 128), (10823, 0), (10444, 128), (11631, 0), (201, 0), (204, 0)]:
+    for kernel, block in [(0, 0), (10, 128), (21, 512), (99, 0), (99, 128), (10823, 0), (10444, 128), (11631, 0), (201, 0), (204, 0), (3000, 0), (3202, 0),
+                          (3104, 0), (400, 0)]:
         with pkg.Lattice(to_param(p), obst, kernel=kernel, block=block) as lat:
             lat.upload(cells0)
             lat.run(9)
