@@ -19,6 +19,7 @@
 #include "lbm_fused2_kernel.cuh"
 #include "lbm_cluster_kernel.cuh"
 #include "lbm_ll_kernel.cuh"
+#include "lbm_band_kernel.cuh"
 
 #include <cudaTypedefs.h>
 #include <unistd.h>
@@ -127,6 +128,10 @@ struct Slab {
     int ll_block = 0;
     size_t ll_smem = 0;
     uint4* ll_packets = nullptr; // [2 directions][2 parities][rows][pitch]
+    // whole runs in one cooperative launch of step_band_kernel: a band of rows per CTA, neighbour flags
+    bool use_band = false;
+    unsigned band_grid = 0;
+    unsigned* band_flags = nullptr; // [band_grid][32]
     // interior rows through step_tma_kernel
     bool use_tma = false;
     CUtensorMap tmap[2];  // per lattice: boxes TMA_TX wide
@@ -168,6 +173,8 @@ struct lbm_lattice {
     void (*tma_kernel)(CUtensorMap, CUtensorMap, TmaArgs) = nullptr; // interior rows (null: `kernel` does every row)
     int tma_ty = 0, tma_stages = 0, tma_minb = 0, tma_resident = 0, sm_count = 0;
     int loop_resident[2] = {0, 0};
+    void (*band_kernel)(BandArgs) = nullptr;       // step_band_kernel (null: not available for this lattice)
+    int band_block = 0, band_resident = 0;
     void (*ll_kernel)(LLArgs) = nullptr;           // step_ll_kernel (null: not available for this lattice)
     unsigned ll_flags = 0;                         // packet flags handed out so far (never reused)
     void (*cluster_kernel)(ClusterArgs) = nullptr; // step_cluster_kernel (null: not available for this lattice)
@@ -304,6 +311,10 @@ bool cluster_by_shape(int cpt, int vert, int maxt, ClusterChoice* c)
 //                cluster of up to 16 CTAs); also the default for single-slab grids of up to CLUSTER_MAX_CELLS cells.
 //                3CVM forces C cells per thread (1, 2, 4), V = 1 both pairs of a thread side by side through the
 //                collision, M x 256 threads per CTA at most (3411 3401 3402 3404 3202 3204 3104)
+//   500          step_band_kernel (all steps of a run in one cooperative launch, a band of rows per CTA, neighbour flags
+//                instead of a grid barrier); also the default for single-slab grids of up to LOOP_MAX_CELLS cells
+//                that step_ll_kernel does not take and that have a row for every resident CTA.  5BM: B x 128 threads per CTA, M CTAs per SM asked of the
+//                compiler (522 514 521; 521 runs both pairs of a thread side by side through the collision)
 //   400          step_ll_kernel (all steps of a run in one cooperative launch, a row per CTA, cells in registers, rows
 //                exchanging flagged 16-byte packets through L2); also the default for single-slab grids of up to
 //                LL_MAX_CELLS cells with nx <= 1024 whose rows are all resident at once
@@ -315,6 +326,8 @@ constexpr long long LOOP_MAX_CELLS = 1400000; // 2 x 36 B x cells <= ~100 MB of 
 constexpr long long LOOP_VEC4_CELLS = 70000;  // up to 256 x 256: one cell per thread (<= 512 CTAs of 128 threads) beats four;
                                               // above, the one-counter grid barrier gets too slow for that many CTAs
 struct KernelChoice {
+    bool band;
+    int band_block, band_minb;
     bool ll;
     bool cluster;
     int cl_cpt, cl_vert, cl_maxt; // 0: chosen from the grid's shape
@@ -326,11 +339,16 @@ struct KernelChoice {
     bool f2;
     int f2_r, f2_srows, f2_stages, f2_minb;
 };
+bool k_band_default(int kernel) { return kernel == 0; }
 KernelChoice choose_kernel(const lbm_options_t& o, int nx)
 {
     KernelChoice k;
     k.vec4 = (nx % 4 == 0) && o.kernel != 99;
-    const bool cl_code = (o.kernel >= 3000 && o.kernel < 4000) || o.kernel == 400; // everything else as the default
+    const bool band_code = (o.kernel >= 500 && o.kernel < 600);
+    const bool cl_code = (o.kernel >= 3000 && o.kernel < 4000) || o.kernel == 400 || band_code; // everything else as the default
+    k.band = k_band_default(o.kernel) || band_code;
+    k.band_block = 128, k.band_minb = 4;
+    if (band_code && o.kernel != 500) k.band_block = 128 * ((o.kernel / 10) % 10), k.band_minb = o.kernel % 10;
     k.ll = (o.kernel == 0 || o.kernel == 400);
     k.cluster = (o.kernel >= 3000 && o.kernel < 4000); // not a default: step_ll_kernel is faster wherever both apply
     k.cl_cpt = k.cl_vert = k.cl_maxt = 0;
@@ -483,6 +501,25 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
         }
         cudaGetLastError();
     }
+    // a band of rows per CTA (cooperative launch, neighbour flags)
+    s.use_band = false;
+    if (k.band && L->band_kernel && !s.use_ll && k.vec4 && L->opt.use_graph && !L->interleaved && total_slabs == 1 && L->nslabs == 1 &&
+        ((L->opt.kernel >= 500 && L->opt.kernel < 600) || nominal_cells <= LOOP_MAX_CELLS)) {
+        long long g = static_cast<long long>(L->band_resident) * L->sm_count;
+        if (const char* t = getenv("LBM_BAND_GRID")) {
+            const long long v = atoll(t);
+            if (v >= 1 && v < g) g = v;
+        }
+        // default: only where every resident CTA gets a row (1024 x 1024: 13.3 us per step against 13.9 from
+        // step_loop_kernel); with fewer rows than CTA slots the tile walk of step_loop_kernel spreads a row over
+        // several CTAs and wins (profiles/r02_small_grids.md)
+        const bool asked = (L->opt.kernel >= 500 && L->opt.kernel < 600);
+        if (g > s.rows) g = asked ? s.rows : 0;
+        if (g >= 1) {
+            s.use_band = true;
+            s.band_grid = static_cast<unsigned>(g);
+        }
+    }
     if (L->opt.kernel == 400 && !s.use_ll && getenv("LBM_DEBUG")) fprintf(stderr, "[lbm] step_ll_kernel asked for but not applicable\n");
     s.use_tma = !s.use_loop && k.tma && L->tma_kernel && s.rows >= 3;
     if (s.use_tma) {
@@ -553,7 +590,7 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
     int slots = 1;
     while (slots < 64 && static_cast<unsigned>(slots) * 1024u < ctas) slots <<= 1;
     s.nslots = slots;
-    if (s.use_ll) s.nslots = LL_SLOTS; // one RED per CTA, step and word: spread them
+    if (s.use_ll || s.use_band) s.nslots = LL_SLOTS; // one RED per CTA, step and word: spread them
 }
 
 // the lattice as a 3-D tensor (x, y, plane) for the TMA unit; boxes are (TMA_TX | TMA_TXW) x box_rows x 1
@@ -1037,6 +1074,25 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
             if (!coop) L->loop_kernel[v] = nullptr;
         }
     }
+    if (k.band && k.vec4 && !L->interleaved && !uses_halo_cfg(L) && L->nslabs == 1) {
+        CU(cudaSetDevice(L->slabs[0].device));
+        int sms = 0, coop = 0;
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, L->slabs[0].device));
+        CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, L->slabs[0].device));
+        L->sm_count = sms;
+        void (*fn)(BandArgs) = nullptr;
+        const int bb = k.band_block, bm = k.band_minb;
+        if (bb == 256 && bm == 2) fn = strict ? step_band_kernel<true, 256, 2, false> : step_band_kernel<false, 256, 2, false>;
+        else if (bb == 128 && bm == 4) fn = strict ? step_band_kernel<true, 128, 4, false> : step_band_kernel<false, 128, 4, false>;
+        else if (bb == 256 && bm == 1) fn = strict ? step_band_kernel<true, 256, 1, true> : step_band_kernel<false, 256, 1, true>;
+        else if (bb == 512 && bm == 1) fn = strict ? step_band_kernel<true, 512, 1, false> : step_band_kernel<false, 512, 1, false>;
+        else return fail(LBM_EINVAL, "no step_band_kernel variant with %d threads and %d CTAs per SM", bb, bm);
+        if (coop) {
+            int resident = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, reinterpret_cast<const void*>(fn), bb, 0));
+            if (resident >= 1) L->band_kernel = fn, L->band_block = bb, L->band_resident = resident;
+        }
+    }
     if (k.ll && !L->interleaved && !uses_halo_cfg(L) && L->nslabs == 1) {
         CU(cudaSetDevice(L->slabs[0].device));
         int sms = 0, coop = 0;
@@ -1177,6 +1233,7 @@ void free_slab(Slab& s)
     cudaFree(s.state_sums);
     cudaFree(s.loop_barrier);
     cudaFree(s.ll_packets);
+    cudaFree(s.band_flags);
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
@@ -1612,9 +1669,14 @@ int lbm_run(lbm_lattice_t* L, int iters)
     const bool use_graphs = L->opt.use_graph && !L->interleaved;
     bool all_loop = true, f2 = true;
     const bool ll = (L->nslabs == 1 && L->slabs[0].use_ll);
-    const bool cluster = !ll && (L->nslabs == 1 && L->slabs[0].use_cluster);
+    const bool band = !ll && (L->nslabs == 1 && L->slabs[0].use_band);
+    const bool cluster = !ll && !band && (L->nslabs == 1 && L->slabs[0].use_cluster);
     for (int i = 0; i < L->nslabs; i++) all_loop = all_loop && L->slabs[i].use_loop, f2 = f2 && L->slabs[i].use_f2;
-    if (cluster || ll) all_loop = true; // no graphs, no per-step launches
+    if (cluster || ll || band) all_loop = true; // no graphs, no per-step launches
+    if (band && !L->slabs[0].band_flags) {
+        CU(cudaSetDevice(L->slabs[0].device));
+        CU(cudaMalloc(&L->slabs[0].band_flags, static_cast<size_t>(L->slabs[0].band_grid) * 32 * sizeof(unsigned)));
+    }
     if (ll) {
         // packet buffers (zeroed: flag 0 is never waited for); flags are never reused by a lattice
         Slab& s = L->slabs[0];
@@ -1699,7 +1761,34 @@ int lbm_run(lbm_lattice_t* L, int iters)
     int done = 0;        // timesteps queued
     long long passes = 0; // lattice swaps queued
     long long epochs = 0; // halo epochs queued after epoch_base
-    if (ll) {
+    if (band) {
+        // every step of this run in ONE cooperative launch of step_band_kernel, a band of rows per CTA
+        Slab& s = L->slabs[0];
+        CU(cudaSetDevice(s.device));
+        BandArgs a;
+        memset(&a, 0, sizeof a);
+        a.lat[0] = s.lat[0], a.lat[1] = s.lat[1];
+        a.pf = plane_floats(L, s);
+        a.obst = s.obst;
+        a.sums = s.sums;
+        a.nslots = s.nslots;
+        a.flags = s.band_flags;
+        a.error = s.error;
+        a.timeout_ns = L->timeout_ns;
+        a.first_step = first, a.nsteps = iters, a.last_step = first + iters - 1;
+        a.src = parity;
+        a.nx = L->p.nx, a.nxv = L->p.nx / 4, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
+        a.accel_row = s.accel_row;
+        a.omega = L->p.omega, a.w1a = L->w1a, a.w2a = L->w2a;
+        CU(cudaMemsetAsync(s.band_flags, 0, static_cast<size_t>(s.band_grid) * 32 * sizeof(unsigned), s.stream));
+        void* kp[1] = {&a};
+        CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(L->band_kernel), dim3(s.band_grid), dim3(static_cast<unsigned>(L->band_block)),
+                                       kp, 0, s.stream));
+        L->launches++;
+        done = iters;
+        passes = iters;
+        epochs = iters;
+    } else if (ll) {
         // every step of this run in ONE cooperative launch of step_ll_kernel, a CTA per row
         Slab& s = L->slabs[0];
         CU(cudaSetDevice(s.device));

@@ -1,10 +1,8 @@
 #!/bin/bash
 # scratch job script for gpurun (rewritten per call)
 mkdir -p gpurun_out
-export LBM_HALO_TIMEOUT_MS=3000
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "strict_steps_bit_exact or av_vels_identical or chunked" > gpurun_out/cl_tests.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/cl_tests.txt
-tail -n 15 gpurun_out/cl_tests.txt
-timeout 300 python tools/small_sweep.py 0 128x128,128x256,256x256 201 400 400::fast 201::fast > gpurun_out/ll_sweep.txt 2>&1
-timeout 300 python tools/small_sweep.py 0 128x128 3411:1 3401:1 3202:1 3411:1:fast >> gpurun_out/ll_sweep.txt 2>&1
-timeout 300 python tools/small_sweep.py 0 128x256 3402:1 >> gpurun_out/ll_sweep.txt 2>&1
-cat gpurun_out/ll_sweep.txt
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r02c_gputest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/r02c_gputest.txt
+tail -n 6 gpurun_out/r02c_gputest.txt
+timeout 900 python bench.py > gpurun_out/r02c_bench_n1.json 2> gpurun_out/r02c_bench_n1.err; echo "bench rc=$?"
+timeout 20 python tools/bench_line.py gpurun_out/r02c_bench_n1.json < /dev/null
+tail -n 3 gpurun_out/r02c_bench_n1.err

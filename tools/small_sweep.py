@@ -21,8 +21,13 @@ def main():
     steps_arg = int(sys.argv[1])
     gin = os.path.join(ROOT, "tests", "golden", "inputs")
     for grid in sys.argv[2].split(","):
-        p = read_params(os.path.join(gin, f"input_{grid}.params"))
-        obst = read_obstacles(os.path.join(gin, f"obstacles_{grid}.dat"), p.nx, p.ny)
+        if os.path.exists(os.path.join(gin, f"input_{grid}.params")):
+            p = read_params(os.path.join(gin, f"input_{grid}.params"))
+            obst = read_obstacles(os.path.join(gin, f"obstacles_{grid}.dat"), p.nx, p.ny)
+        else:  # a synthetic channel of that size
+            nx, ny = (int(v) for v in grid.split("x"))
+            p = make_param(nx, ny, 1000)
+            obst = pkg.channel_obstacles(nx, ny)
         steps = steps_arg if steps_arg > 0 else p.maxIters
         ref = None
         for spec in sys.argv[3:]:
