@@ -1,8 +1,8 @@
 #!/bin/bash
 # scratch job script for gpurun (rewritten per call)
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r02c_gputest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/r02c_gputest.txt
-tail -n 6 gpurun_out/r02c_gputest.txt
-timeout 900 python bench.py > gpurun_out/r02c_bench_n1.json 2> gpurun_out/r02c_bench_n1.err; echo "bench rc=$?"
-timeout 20 python tools/bench_line.py gpurun_out/r02c_bench_n1.json < /dev/null
-tail -n 3 gpurun_out/r02c_bench_n1.err
+timeout 400 python -m pytest tests/test_gpu_multi.py -m gpu -q > gpurun_out/r02c_gputest_multi.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/r02c_gputest_multi.txt
+tail -n 3 gpurun_out/r02c_gputest_multi.txt
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 10 > gpurun_out/r02c_bench_n2.json 2> gpurun_out/r02c_bench_n2.err; echo "bench rc=$?"
+timeout 20 python tools/bench_line.py gpurun_out/r02c_bench_n2.json < /dev/null
+tail -n 3 gpurun_out/r02c_bench_n2.err
