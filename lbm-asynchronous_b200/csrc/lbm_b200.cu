@@ -125,9 +125,14 @@ struct Slab {
     size_t cl_smem = 0;
     // whole runs in one cooperative launch of step_ll_kernel: a row per CTA, cells in registers, packets through L2
     bool use_ll = false;
+    int ll_var = 0;              // 0: one cell per thread, 1: four
     int ll_block = 0;
     size_t ll_smem = 0;
     uint4* ll_packets = nullptr; // [2 directions][2 parities][rows][pitch]
+    uint4* ll_recv_s = nullptr;  // row slabs: packet areas [2][pitch] inside halo_block, written by the neighbours
+    uint4* ll_recv_n = nullptr;
+    uint4* peer_ll_s = nullptr;  // the south neighbour's ll_recv_n / the north neighbour's ll_recv_s (peer memory)
+    uint4* peer_ll_n = nullptr;
     // whole runs in one cooperative launch of step_band_kernel: a band of rows per CTA, neighbour flags
     bool use_band = false;
     unsigned band_grid = 0;
@@ -175,7 +180,8 @@ struct lbm_lattice {
     int loop_resident[2] = {0, 0};
     void (*band_kernel)(BandArgs) = nullptr;       // step_band_kernel (null: not available for this lattice)
     int band_block = 0, band_resident = 0;
-    void (*ll_kernel)(LLArgs) = nullptr;           // step_ll_kernel (null: not available for this lattice)
+    void (*ll_kernel[2])(LLArgs) = {nullptr, nullptr}; // step_ll_kernel, 1 / 4 cells per thread (null: not available)
+    int ll_resident[2] = {0, 0};                   // resident CTAs per SM at the lattice's row length
     unsigned ll_flags = 0;                         // packet flags handed out so far (never reused)
     void (*cluster_kernel)(ClusterArgs) = nullptr; // step_cluster_kernel (null: not available for this lattice)
     int cl_cpt = 0, cl_vert = 0, cl_maxt = 0;      // its cells per thread, collision shape, thread limit
@@ -316,9 +322,12 @@ bool cluster_by_shape(int cpt, int vert, int maxt, ClusterChoice* c)
 //                that step_ll_kernel does not take and that have a row for every resident CTA.  5BM: B x 128 threads per CTA, M CTAs per SM asked of the
 //                compiler (522 514 521; 521 runs both pairs of a thread side by side through the collision)
 //   400          step_ll_kernel (all steps of a run in one cooperative launch, a row per CTA, cells in registers, rows
-//                exchanging flagged 16-byte packets through L2); also the default for single-slab grids of up to
-//                LL_MAX_CELLS cells with nx <= 1024 whose rows are all resident at once
-constexpr long long LL_MAX_CELLS = 70000; // up to 256 x 256
+//                exchanging flagged 16-byte packets through L2, slabs on several GPUs through each other's memory); also
+//                the default for slabs of up to LL_MAX_CELLS cells (one cell per thread, nx <= 1024) or LL4_MAX_CELLS
+//                cells (four cells per thread, nx <= 1024) whose rows are all resident at once.  401 / 404 force one /
+//                four cells per thread
+constexpr long long LL_MAX_CELLS = 70000;   // up to 256 x 256: one cell per thread
+constexpr long long LL4_MAX_CELLS = 300000; // up to 1024 x 256 (a quarter of the shipped 1024 x 1024 case): four
 constexpr int LL_SLOTS = 8;               // slots of the per-step sums (one RED per CTA, step and word)
 constexpr long long CLUSTER_MAX_CELLS = 32768; // 128 x 256: above, 16 SMs have more arithmetic than the whole GPU has latency
 constexpr int CLUSTER_MAX_CTAS = 16;
@@ -345,11 +354,12 @@ KernelChoice choose_kernel(const lbm_options_t& o, int nx)
     KernelChoice k;
     k.vec4 = (nx % 4 == 0) && o.kernel != 99;
     const bool band_code = (o.kernel >= 500 && o.kernel < 600);
-    const bool cl_code = (o.kernel >= 3000 && o.kernel < 4000) || o.kernel == 400 || band_code; // everything else as the default
+    const bool ll_code = (o.kernel == 400 || o.kernel == 401 || o.kernel == 404);
+    const bool cl_code = (o.kernel >= 3000 && o.kernel < 4000) || ll_code || band_code; // everything else as the default
     k.band = k_band_default(o.kernel) || band_code;
     k.band_block = 128, k.band_minb = 4;
     if (band_code && o.kernel != 500) k.band_block = 128 * ((o.kernel / 10) % 10), k.band_minb = o.kernel % 10;
-    k.ll = (o.kernel == 0 || o.kernel == 400);
+    k.ll = (o.kernel == 0 || ll_code);
     k.cluster = (o.kernel >= 3000 && o.kernel < 4000); // not a default: step_ll_kernel is faster wherever both apply
     k.cl_cpt = k.cl_vert = k.cl_maxt = 0;
     if (k.cluster && o.kernel != 3000) k.cl_cpt = (o.kernel / 100) % 10, k.cl_vert = (o.kernel / 10) % 10, k.cl_maxt = 256 * (o.kernel % 10);
@@ -487,19 +497,29 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
     s.use_cluster = false;
     if (k.cluster && L->cluster_kernel && L->opt.use_graph && !L->interleaved && total_slabs == 1 && L->nslabs == 1 && s.cl_size > 0)
         s.use_cluster = true;
-    // a row per CTA, all rows resident (cooperative launch)
+    // a row per CTA, all rows resident (cooperative launch).  With several slabs every slab needs a GPU of its own
+    // (the resident kernels wait for one another's packets) and every rank must take the same decision: it is based on
+    // the nominal slab height
     s.use_ll = false;
-    if (k.ll && L->ll_kernel && L->opt.use_graph && !L->interleaved && total_slabs == 1 && L->nslabs == 1 && L->p.nx <= 1024 &&
-        (L->opt.kernel == 400 || nominal_cells <= LL_MAX_CELLS)) {
-        const int block = (L->p.nx + 31) / 32 * 32;
-        const size_t smem = (2 * 6 * static_cast<size_t>(block) + 2 * (block / 32) * 4) * sizeof(float);
-        int resident = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, reinterpret_cast<const void*>(L->ll_kernel), block, smem) == cudaSuccess &&
-            static_cast<long long>(resident) * L->sm_count >= s.rows) {
-            s.use_ll = true;
-            s.ll_block = block, s.ll_smem = smem;
+    {
+        const bool ll_asked = (L->opt.kernel == 400 || L->opt.kernel == 401 || L->opt.kernel == 404);
+        const int nominal_rows = (L->p.ny + total_slabs - 1) / total_slabs;
+        const bool halo_ok = !uses_halo_cfg(L) || (L->opt.halo_mode == LBM_HALO_SYNC && L->opt.halo_lag == 0);
+        if (k.ll && L->opt.use_graph && !L->interleaved && halo_ok) {
+            for (int v = 0; v < 2 && !s.use_ll; v++) {
+                if (!L->ll_kernel[v]) continue;
+                if (L->opt.kernel == 401 && v != 0) continue;
+                if (L->opt.kernel == 404 && v != 1) continue;
+                if (!ll_asked && nominal_cells > (v ? LL4_MAX_CELLS : LL_MAX_CELLS)) continue;
+                if (static_cast<long long>(L->ll_resident[v]) * L->sm_count < nominal_rows) continue;
+                const int block = (L->p.nx / (v ? 4 : 1) + 31) / 32 * 32;
+                s.use_ll = true;
+                s.ll_var = v;
+                s.ll_block = block;
+                s.ll_smem = (2 * 6 * static_cast<size_t>(block) + 2 * (block / 32) * 4) * sizeof(float);
+            }
         }
-        cudaGetLastError();
+        if (ll_asked && !s.use_ll && getenv("LBM_DEBUG")) fprintf(stderr, "[lbm] step_ll_kernel asked for but not applicable\n");
     }
     // a band of rows per CTA (cooperative launch, neighbour flags)
     s.use_band = false;
@@ -520,7 +540,6 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
             s.band_grid = static_cast<unsigned>(g);
         }
     }
-    if (L->opt.kernel == 400 && !s.use_ll && getenv("LBM_DEBUG")) fprintf(stderr, "[lbm] step_ll_kernel asked for but not applicable\n");
     s.use_tma = !s.use_loop && k.tma && L->tma_kernel && s.rows >= 3;
     if (s.use_tma) {
         const int interior = s.rows - 2;
@@ -726,8 +745,14 @@ int alloc_halo(lbm_lattice* L, Slab& s)
     CU(cudaSetDevice(s.device));
     const size_t ring_floats = ring_floats_of(L);
     const size_t obst_bytes = 2 * static_cast<size_t>(L->opitch) * sizeof(uint32_t);
-    s.halo_bytes = 2 * ring_floats * sizeof(float) + 2 * 128 + obst_bytes;
+    const size_t ll_off = (2 * ring_floats * sizeof(float) + 2 * 128 + obst_bytes + 15) / 16 * 16;
+    const size_t ll_bytes = 2 * static_cast<size_t>(L->pitch) * sizeof(uint4); // one boundary: [2 parities][pitch] packets
+    s.halo_bytes = ll_off + 2 * ll_bytes;
     CU(cudaMalloc(&s.halo_block, s.halo_bytes));
+    // step_ll_kernel's packet areas: zeroed here, before anybody can know the address (flag 0 is never waited for)
+    s.ll_recv_s = reinterpret_cast<uint4*>(s.halo_block + ll_off);
+    s.ll_recv_n = reinterpret_cast<uint4*>(s.halo_block + ll_off + ll_bytes);
+    CU(cudaMemsetAsync(s.ll_recv_s, 0, 2 * ll_bytes, s.stream));
     s.ring_s = reinterpret_cast<float*>(s.halo_block);
     s.ring_n = s.ring_s + ring_floats;
     s.flag_s = reinterpret_cast<unsigned long long*>(s.halo_block + 2 * ring_floats * sizeof(float));
@@ -1093,16 +1118,35 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
             if (resident >= 1) L->band_kernel = fn, L->band_block = bb, L->band_resident = resident;
         }
     }
-    if (k.ll && !L->interleaved && !uses_halo_cfg(L) && L->nslabs == 1) {
-        CU(cudaSetDevice(L->slabs[0].device));
-        int sms = 0, coop = 0;
-        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, L->slabs[0].device));
-        CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, L->slabs[0].device));
-        L->sm_count = sms;
-        if (coop) {
-            L->ll_kernel = strict ? step_ll_kernel<true> : step_ll_kernel<false>;
-            CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(L->ll_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    if (k.ll && !L->interleaved) {
+        const bool halo = uses_halo_cfg(L);
+        void (*fn[2])(LLArgs);
+        if (halo) {
+            fn[0] = strict ? step_ll_kernel<true, 1, false, 1024, 1, true> : step_ll_kernel<false, 1, false, 1024, 1, true>;
+            fn[1] = strict ? step_ll_kernel<true, 4, false, 256, 2, true> : step_ll_kernel<false, 4, false, 256, 2, true>;
+        } else {
+            fn[0] = strict ? step_ll_kernel<true, 1, false, 1024, 1, false> : step_ll_kernel<false, 1, false, 1024, 1, false>;
+            fn[1] = strict ? step_ll_kernel<true, 4, false, 256, 2, false> : step_ll_kernel<false, 4, false, 256, 2, false>;
         }
+        for (int i = 0; i < L->nslabs; i++) {
+            CU(cudaSetDevice(L->slabs[i].device));
+            int sms = 0, coop = 0;
+            CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, L->slabs[i].device));
+            CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, L->slabs[i].device));
+            if (i == 0 || sms < L->sm_count) L->sm_count = sms;
+            for (int v = 0; v < 2; v++) {
+                const int cpt = v ? 4 : 1;
+                int resident = 0;
+                if (coop && params->nx % cpt == 0 && params->nx / cpt <= (v ? 256 : 1024)) {
+                    const int block = (params->nx / cpt + 31) / 32 * 32;
+                    const size_t smem = (2 * 6 * static_cast<size_t>(block) + 2 * (block / 32) * 4) * sizeof(float);
+                    CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn[v]), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, reinterpret_cast<const void*>(fn[v]), block, smem));
+                }
+                if (i == 0 || resident < L->ll_resident[v]) L->ll_resident[v] = resident;
+            }
+        }
+        for (int v = 0; v < 2; v++) L->ll_kernel[v] = L->ll_resident[v] > 0 ? fn[v] : nullptr;
     }
     if (k.cluster && !L->interleaved && !uses_halo_cfg(L) && L->nslabs == 1) {
         // one cluster of C CTAs (a power of two <= 16 and <= rows), rows dealt out in blocks of rpc = ceil(rows / C)
@@ -1283,7 +1327,8 @@ int push_boundary_rows(lbm_lattice* L, Slab& s)
 int32_t halo_config_word(const lbm_lattice* L)
 {
     return static_cast<int32_t>((L->opt.arith & 0xf) | ((L->opt.halo_mode & 0xf) << 4) | ((L->opt.halo_lag & 0xff) << 8) |
-                                ((L->slabs[0].use_f2 ? 1 : 0) << 16) | ((L->slabs[0].use_loop ? 1 : 0) << 17));
+                                ((L->slabs[0].use_f2 ? 1 : 0) << 16) | ((L->slabs[0].use_loop ? 1 : 0) << 17) |
+                                ((L->slabs[0].use_ll ? 1 + L->slabs[0].ll_var : 0) << 18));
 }
 
 // the halo protocol stores and adds into the neighbour device's memory from inside kernels: peer access is not
@@ -1473,6 +1518,7 @@ static int create_on_impl(const lbm_param_t* params, const void* obstacles, bool
             if (rc) break;
             s.peer_ring_s = south.ring_n, s.peer_flag_s = south.flag_n;
             s.peer_ring_n = north.ring_s, s.peer_flag_n = north.flag_s;
+            s.peer_ll_s = south.ll_recv_n, s.peer_ll_n = north.ll_recv_s;
             rc = fetch_halo_obstacles(L, s, south.edge_obst, north.edge_obst);
         }
         if (rc) {
@@ -1632,6 +1678,11 @@ int lbm_halo_connect(lbm_lattice_t* L, const void* south_handle, const void* nor
     // my south neighbour receives my row 0 in ITS north ring; my north neighbour my last row in ITS south ring
     s.peer_ring_s = ring_n_of(base[0]), s.peer_flag_s = flag_n_of(base[0]);
     s.peer_ring_n = ring_s_of(base[1]), s.peer_flag_n = flag_s_of(base[1]);
+    {
+        const size_t ll_off = reinterpret_cast<char*>(s.ll_recv_s) - s.halo_block, ll_bytes = 2 * static_cast<size_t>(L->pitch) * sizeof(uint4);
+        s.peer_ll_s = reinterpret_cast<uint4*>(base[0] + ll_off + ll_bytes); // the south neighbour's ll_recv_n
+        s.peer_ll_n = reinterpret_cast<uint4*>(base[1] + ll_off);            // the north neighbour's ll_recv_s
+    }
     auto edge_obst_of = [&](char* b) { return reinterpret_cast<const uint32_t*>(b + 2 * ring_floats * sizeof(float) + 256); };
     int rc = fetch_halo_obstacles(L, s, edge_obst_of(base[0]), edge_obst_of(base[1]));
     if (rc) return rc;
@@ -1668,7 +1719,8 @@ int lbm_run(lbm_lattice_t* L, int iters)
     const int parity = L->cur;
     const bool use_graphs = L->opt.use_graph && !L->interleaved;
     bool all_loop = true, f2 = true;
-    const bool ll = (L->nslabs == 1 && L->slabs[0].use_ll);
+    bool ll = true;
+    for (int i = 0; i < L->nslabs; i++) ll = ll && L->slabs[i].use_ll;
     const bool band = !ll && (L->nslabs == 1 && L->slabs[0].use_band);
     const bool cluster = !ll && !band && (L->nslabs == 1 && L->slabs[0].use_cluster);
     for (int i = 0; i < L->nslabs; i++) all_loop = all_loop && L->slabs[i].use_loop, f2 = f2 && L->slabs[i].use_f2;
@@ -1678,18 +1730,22 @@ int lbm_run(lbm_lattice_t* L, int iters)
         CU(cudaMalloc(&L->slabs[0].band_flags, static_cast<size_t>(L->slabs[0].band_grid) * 32 * sizeof(unsigned)));
     }
     if (ll) {
+        f2 = false;
         // packet buffers (zeroed: flag 0 is never waited for); flags are never reused by a lattice
-        Slab& s = L->slabs[0];
-        CU(cudaSetDevice(s.device));
-        const size_t bytes = 4 * static_cast<size_t>(s.rows) * L->pitch * sizeof(uint4);
-        if (!s.ll_packets) {
-            CU(cudaMalloc(&s.ll_packets, bytes));
-            CU(cudaMemsetAsync(s.ll_packets, 0, bytes, s.stream));
-            L->ll_flags = 0;
-        } else if (static_cast<unsigned long long>(L->ll_flags) + static_cast<unsigned long long>(iters) + 1ull > 0xffffffffull) {
-            CU(cudaMemsetAsync(s.ll_packets, 0, bytes, s.stream));
-            L->ll_flags = 0;
+        const bool wrap = static_cast<unsigned long long>(L->ll_flags) + static_cast<unsigned long long>(iters) + 2ull > 0x7fffffffull;
+        if (wrap && uses_halo(L)) return fail(LBM_EINVAL, "packet flags exhausted (2^31 steps on one multi-GPU lattice)");
+        for (int i = 0; i < L->nslabs; i++) {
+            Slab& s = L->slabs[i];
+            CU(cudaSetDevice(s.device));
+            const size_t bytes = 4 * static_cast<size_t>(s.rows) * L->pitch * sizeof(uint4);
+            if (!s.ll_packets) {
+                CU(cudaMalloc(&s.ll_packets, bytes));
+                CU(cudaMemsetAsync(s.ll_packets, 0, bytes, s.stream));
+            } else if (wrap) {
+                CU(cudaMemsetAsync(s.ll_packets, 0, bytes, s.stream));
+            }
         }
+        if (wrap) L->ll_flags = 0;
     }
     // everything that can fail without having touched the lattice comes first: a failure here leaves the run
     // un-started and the call can be repeated
@@ -1789,31 +1845,54 @@ int lbm_run(lbm_lattice_t* L, int iters)
         passes = iters;
         epochs = iters;
     } else if (ll) {
-        // every step of this run in ONE cooperative launch of step_ll_kernel, a CTA per row
-        Slab& s = L->slabs[0];
-        CU(cudaSetDevice(s.device));
-        LLArgs a;
-        memset(&a, 0, sizeof a);
-        a.lat[0] = s.lat[0], a.lat[1] = s.lat[1];
-        a.pf = plane_floats(L, s);
-        a.obst = s.obst;
-        a.sums = s.sums;
-        a.nslots = s.nslots;
-        const size_t half = 2 * static_cast<size_t>(s.rows) * L->pitch;
-        a.pk_north = s.ll_packets, a.pk_south = s.ll_packets + half;
-        a.flag_base = L->ll_flags;
-        a.error = s.error;
-        a.timeout_ns = L->timeout_ns;
-        a.first_step = first, a.nsteps = iters, a.last_step = first + iters - 1;
-        a.src = parity;
-        a.nx = L->p.nx, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
-        a.accel_row = s.accel_row;
-        a.omega = L->p.omega, a.w1a = L->w1a, a.w2a = L->w2a;
-        void* kp[1] = {&a};
-        CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(L->ll_kernel), dim3(static_cast<unsigned>(s.rows)),
-                                       dim3(static_cast<unsigned>(s.ll_block)), kp, s.ll_smem, s.stream));
-        L->ll_flags += static_cast<unsigned>(iters);
-        L->launches++;
+        // every step of this run in ONE cooperative launch of step_ll_kernel per slab, a CTA per row; slabs on
+        // different GPUs run at the same time and exchange packets (the seed packets of the current state first)
+        const unsigned seed_flag = L->ll_flags + 1u, flag_base = L->ll_flags + 1u;
+        if (uses_halo(L))
+            for (int i = 0; i < L->nslabs; i++) {
+                Slab& s = L->slabs[i];
+                CU(cudaSetDevice(s.device));
+                LLSeedArgs sa;
+                sa.lat = s.lat[parity];
+                sa.pf = plane_floats(L, s);
+                sa.halo_send_s = s.peer_ll_s, sa.halo_send_n = s.peer_ll_n;
+                sa.seed_flag = seed_flag;
+                sa.nx = L->p.nx, sa.rows = s.rows, sa.pitch = L->pitch;
+                ll_seed_kernel<<<(L->p.nx + 127) / 128, 128, 0, s.stream>>>(sa);
+                L->launches++;
+                CU(cudaGetLastError());
+            }
+        for (int i = 0; i < L->nslabs; i++) {
+            Slab& s = L->slabs[i];
+            CU(cudaSetDevice(s.device));
+            LLArgs a;
+            memset(&a, 0, sizeof a);
+            a.lat[0] = s.lat[0], a.lat[1] = s.lat[1];
+            a.pf = plane_floats(L, s);
+            a.obst = s.obst;
+            a.sums = s.sums;
+            a.nslots = s.nslots;
+            const size_t half = 2 * static_cast<size_t>(s.rows) * L->pitch;
+            a.pk_north = s.ll_packets, a.pk_south = s.ll_packets + half;
+            if (uses_halo(L)) {
+                a.halo_recv_s = s.ll_recv_s, a.halo_recv_n = s.ll_recv_n;
+                a.halo_send_s = s.peer_ll_s, a.halo_send_n = s.peer_ll_n;
+            }
+            a.seed_flag = seed_flag;
+            a.flag_base = flag_base;
+            a.error = s.error;
+            a.timeout_ns = L->timeout_ns;
+            a.first_step = first, a.nsteps = iters, a.last_step = first + iters - 1;
+            a.src = parity;
+            a.nx = L->p.nx, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
+            a.accel_row = s.accel_row;
+            a.omega = L->p.omega, a.w1a = L->w1a, a.w2a = L->w2a;
+            void* kp[1] = {&a};
+            CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(L->ll_kernel[s.ll_var]), dim3(static_cast<unsigned>(s.rows)),
+                                           dim3(static_cast<unsigned>(s.ll_block)), kp, s.ll_smem, s.stream));
+            L->launches++;
+        }
+        L->ll_flags += static_cast<unsigned>(iters) + 1u;
         done = iters;
         passes = iters;
         epochs = iters;

@@ -20,12 +20,19 @@
 //     sums in shared memory are added up one step later by three threads and go to sums[step][slot] with one RED each;
 //   * accelerate-at-store as in the other kernels (applied before the exchange); the last step of the launch stores
 //     the cell to the destination lattice in global memory.
+//   * CPT = 4: a thread owns four consecutive cells (packed collision of lbm_collide4.cuh, four packets per direction):
+//     rows of up to 4096 cells, a quarter of the threads -- grids with more rows than CTAs of nx threads can be resident;
+//   * row slabs on several GPUs (HALO): the slab's first / last row store their packets straight into the neighbour
+//     GPU's packet area (peer memory over NVLink, st.relaxed.sys.b128) and poll their own, which the neighbour
+//     writes -- the same protocol at system scope, replacing MPI_Isend/Irecv/Waitall of MPI_Waitall/d2q9-bgk.c:225-253
+//     for small slabs.  A run starts with ll_seed_kernel sending the packets of the CURRENT state (no step produced
+//     them), which the boundary rows' first gather waits for: that is also what lines the GPUs up.
 // Cooperative launch: every CTA must be resident (rows <= resident CTAs), which also bounds the grids it takes.
 // A poll that does not complete within the lattice's time-out sets the error word and gives up (lbm_sync reports it).
 // Replaces the timestep loop of SerialCode/d2q9-bgk.c:187-194 for small single-GPU grids.
 #pragma once
 
-#include "lbm_kernels.cuh"
+#include "lbm_cluster_kernel.cuh" // cells_relax / cells_speed: the collision in two halves
 
 namespace lbm {
 
@@ -37,6 +44,12 @@ struct LLArgs {
     int nslots;
     uint4* pk_north;     // [2][rows][pitch] packets of row r for row r+1
     uint4* pk_south;     // [2][rows][pitch] packets of row r for row r-1
+    // row slabs on several GPUs (HALO): packet areas [2][pitch] of the slab's two boundaries
+    const uint4* halo_recv_s; // what the south neighbour's last row sends up (it writes it: peer stores)
+    const uint4* halo_recv_n; // what the north neighbour's first row sends down
+    uint4* halo_send_s;       // the south neighbour's halo_recv_n (peer memory)
+    uint4* halo_send_n;       // the north neighbour's halo_recv_s
+    unsigned seed_flag;  // flag of the packets ll_seed_kernel sent for the state before first_step (parity slot 1)
     unsigned flag_base;  // flag of step s of this launch = flag_base + s + 1 (never reused by a lattice)
     int* error;
     unsigned long long timeout_ns;
@@ -47,40 +60,89 @@ struct LLArgs {
     float omega, w1a, w2a;
 };
 
+template <bool SYS>
 __device__ __forceinline__ void st_packet(uint4* p, float a, float b, float c, unsigned flag)
 {
-    asm volatile(
-        "{\n\t.reg .b128 q;\n\t.reg .b64 lo, hi;\n\t"
-        "mov.b64 lo, {%1,%2};\n\tmov.b64 hi, {%3,%4};\n\tmov.b128 q, {lo, hi};\n\t"
-        "st.relaxed.gpu.global.b128 [%0], q;\n\t}" ::"l"(p),
-        "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(flag)
-        : "memory");
+    if constexpr (SYS) {
+        asm volatile(
+            "{\n\t.reg .b128 q;\n\t.reg .b64 lo, hi;\n\t"
+            "mov.b64 lo, {%1,%2};\n\tmov.b64 hi, {%3,%4};\n\tmov.b128 q, {lo, hi};\n\t"
+            "st.relaxed.sys.global.b128 [%0], q;\n\t}" ::"l"(p),
+            "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(flag)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .b128 q;\n\t.reg .b64 lo, hi;\n\t"
+            "mov.b64 lo, {%1,%2};\n\tmov.b64 hi, {%3,%4};\n\tmov.b128 q, {lo, hi};\n\t"
+            "st.relaxed.gpu.global.b128 [%0], q;\n\t}" ::"l"(p),
+            "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(flag)
+            : "memory");
+    }
 }
+template <bool SYS>
 __device__ __forceinline__ uint4 ld_packet(const uint4* p)
 {
     uint4 v;
-    asm volatile(
-        "{\n\t.reg .b128 q;\n\t.reg .b64 lo, hi;\n\t"
-        "ld.relaxed.gpu.global.b128 q, [%4];\n\t"
-        "mov.b128 {lo, hi}, q;\n\tmov.b64 {%0,%1}, lo;\n\tmov.b64 {%2,%3}, hi;\n\t}"
-        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-        : "l"(p)
-        : "memory");
+    if constexpr (SYS) {
+        asm volatile(
+            "{\n\t.reg .b128 q;\n\t.reg .b64 lo, hi;\n\t"
+            "ld.relaxed.sys.global.b128 q, [%4];\n\t"
+            "mov.b128 {lo, hi}, q;\n\tmov.b64 {%0,%1}, lo;\n\tmov.b64 {%2,%3}, hi;\n\t}"
+            : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+            : "l"(p)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .b128 q;\n\t.reg .b64 lo, hi;\n\t"
+            "ld.relaxed.gpu.global.b128 q, [%4];\n\t"
+            "mov.b128 {lo, hi}, q;\n\tmov.b64 {%0,%1}, lo;\n\tmov.b64 {%2,%3}, hi;\n\t}"
+            : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+            : "l"(p)
+            : "memory");
+    }
     return v;
 }
 
-// |u| of a cell's new populations (SerialCode:425-452)
-template <bool STRICT>
-__device__ __forceinline__ float speed_cell(const float c[Q])
+// Wait for the N packets at ps[0..N) and pn[0..N) to carry `flag` (sys_s / sys_n: written by a peer GPU).  Every
+// missing packet is re-read per round, all loads of a round in flight together.  Gives up (lost = true, error word
+// set) when the lattice's time-out passes: the run is lost, later waits return at once.
+template <int N, bool HALO>
+__device__ __forceinline__ void wait_packets(const uint4* ps, const uint4* pn, bool want_s, bool want_n, bool sys_s, bool sys_n, unsigned flag,
+                                             uint4 (&S)[N], uint4 (&NN)[N], bool& lost, const LLArgs& a)
 {
-    if constexpr (STRICT) return speed_strict(c);
-    else return speed_fast_guarded(c);
+    unsigned pending = 0u;
+    if (want_s) pending |= (1u << N) - 1u;
+    if (want_n) pending |= ((1u << N) - 1u) << N;
+    unsigned long long t0 = 0ull;
+    unsigned spins = 0;
+    while (true) {
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            if (pending & (1u << j)) S[j] = (HALO && sys_s) ? ld_packet<true>(ps + j) : ld_packet<false>(ps + j);
+            if (pending & (1u << (N + j))) NN[j] = (HALO && sys_n) ? ld_packet<true>(pn + j) : ld_packet<false>(pn + j);
+        }
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            if ((pending & (1u << j)) && S[j].w == flag) pending &= ~(1u << j);
+            if ((pending & (1u << (N + j))) && NN[j].w == flag) pending &= ~(1u << (N + j));
+        }
+        if (pending == 0u || lost) break;
+        if ((++spins & 255u) == 0u) { // not on the fast path: the clock and the error word cost an L2 round trip
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0ull) t0 = now;
+            if (now - t0 > a.timeout_ns || *reinterpret_cast<volatile const int*>(a.error)) {
+                atomicExch(a.error, 1);
+                lost = true;
+                break;
+            }
+        }
+    }
 }
 
-// dynamic shared memory: float xch[2][6][blockDim.x] (sideways populations, ping-pong by step parity)
+// dynamic shared memory: float xch[2][6][blockDim.x] (what leaves a thread's cells sideways, ping-pong by step parity)
 //                        + unsigned part[2][blockDim.x / 32][4] (per-warp |u| sums, ping-pong)
-template <bool STRICT>
-__global__ void __launch_bounds__(1024) step_ll_kernel(const LLArgs a)
+template <bool STRICT, int CPT, bool VERT, int MAXT, int MINB, bool HALO>
+__global__ void __launch_bounds__(MAXT, MINB) step_ll_kernel(const LLArgs a)
 {
     extern __shared__ __align__(16) float ll_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -89,72 +151,119 @@ __global__ void __launch_bounds__(1024) step_ll_kernel(const LLArgs a)
     unsigned* part = reinterpret_cast<unsigned*>(ll_smem + 2 * 6 * nthr);
 
     const int nx = a.nx, y = blockIdx.x;
-    const bool valid = tid < nx;
-    const int x = valid ? tid : nx - 1;
-    const int xw = (x == 0) ? nx - 1 : x - 1; // SerialCode:259-262
-    const int xe = (x == nx - 1) ? 0 : x + 1;
+    const int ipr = nx / CPT; // threads that own cells
+    const bool valid = tid < ipr;
+    const int xi = valid ? tid : ipr - 1;
+    const int x0 = xi * CPT;
+    const int tw = (xi == 0) ? ipr - 1 : xi - 1; // the threads that own the cells west / east of mine (periodic, SerialCode:259-262)
+    const int te = (xi == ipr - 1) ? 0 : xi + 1;
     const int ys = (y == 0) ? a.rows - 1 : y - 1; // :257-258
     const int yn = (y == a.rows - 1) ? 0 : y + 1;
     const size_t pitch = a.pitch;
-    const bool solid = (__ldg(a.obst + static_cast<size_t>(y) * a.opitch + (x >> 5)) >> (x & 31)) & 1u;
+    const uint32_t obits = (__ldg(a.obst + static_cast<size_t>(y) * a.opitch + (x0 >> 5)) >> (x0 & 31)) & ((1u << CPT) - 1u);
     const bool on_accel_row = (y == a.accel_row);
+    const bool peer_s = HALO && (y == 0), peer_n = HALO && (y == a.rows - 1); // rows whose neighbour row lives on another GPU
 
-    // the populations that stream into the cell at first_step: pulled from the source lattice
-    float t[Q];
+    const size_t rows_pitch = static_cast<size_t>(a.rows) * pitch;
+    // where my packets go / come from, parity slot 0; + par * stride for the other
+    uint4* const my_north = peer_n ? a.halo_send_n + x0 : a.pk_north + static_cast<size_t>(y) * pitch + x0;
+    uint4* const my_south = peer_s ? a.halo_send_s + x0 : a.pk_south + static_cast<size_t>(y) * pitch + x0;
+    const uint4* const from_south = peer_s ? a.halo_recv_s + x0 : a.pk_north + static_cast<size_t>(ys) * pitch + x0;
+    const uint4* const from_north = peer_n ? a.halo_recv_n + x0 : a.pk_south + static_cast<size_t>(yn) * pitch + x0;
+    const size_t stride_s = peer_s ? pitch : rows_pitch, stride_n = peer_n ? pitch : rows_pitch;
+    bool lost = false;
+
+    // the populations that stream into the cells at first_step: pulled from the source lattice; across a slab
+    // boundary from the packets ll_seed_kernel of the neighbouring GPU sent (parity slot 1)
+    float t[Q][CPT];
     {
         const float* in = a.lat[a.src & 1];
-        const int col[Q] = {x, xw, x, xe, x, xw, xe, xe, xw};
-        const int row[Q] = {y, y, ys, y, yn, ys, ys, yn, yn};
 #pragma unroll
-        for (int k = 0; k < Q; k++) t[k] = __ldcg(in + k * a.pf + static_cast<size_t>(row[k]) * pitch + col[k]);
+        for (int j = 0; j < CPT; j++) {
+            const int x = x0 + j;
+            const int xw = (x == 0) ? nx - 1 : x - 1, xe = (x == nx - 1) ? 0 : x + 1;
+            const int col[Q] = {x, xw, x, xe, x, xw, xe, xe, xw};
+            const int row[Q] = {y, y, ys, y, yn, ys, ys, yn, yn};
+#pragma unroll
+            for (int k = 0; k < Q; k++) t[k][j] = __ldcg(in + k * a.pf + static_cast<size_t>(row[k]) * pitch + col[k]);
+        }
+        if (HALO && (peer_s || peer_n)) {
+            uint4 S[CPT], N[CPT];
+            wait_packets<CPT, HALO>(from_south + stride_s, from_north + stride_n, peer_s, peer_n, true, true, a.seed_flag, S, N, lost, a);
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                if (peer_s) t[2][j] = __uint_as_float(S[j].x), t[5][j] = __uint_as_float(S[j].y), t[6][j] = __uint_as_float(S[j].z);
+                if (peer_n) t[4][j] = __uint_as_float(N[j].x), t[7][j] = __uint_as_float(N[j].y), t[8][j] = __uint_as_float(N[j].z);
+            }
+        }
     }
     float* out = a.lat[(a.src + a.nsteps) & 1];
-    const size_t rows_pitch = static_cast<size_t>(a.rows) * pitch;
-    uint4* const my_north = a.pk_north + static_cast<size_t>(y) * pitch + x;
-    uint4* const my_south = a.pk_south + static_cast<size_t>(y) * pitch + x;
-    const uint4* const from_south = a.pk_north + static_cast<size_t>(ys) * pitch + x; // what the row below sends up
-    const uint4* const from_north = a.pk_south + static_cast<size_t>(yn) * pitch + x; // what the row above sends down
-    bool lost = false;
 
     for (int s = 0; s < a.nsteps; s++) {
         const int par = s & 1;
         const bool last = (s + 1 == a.nsteps);
-        // ---- collision / bounce-back (update_cell without |u|), accelerate_flow() of the next step
-        float c[Q], o[Q];
-        collide_cell<STRICT, false>(t, a.omega, c);
-        o[0] = solid ? t[0] : c[0];
-        o[1] = solid ? t[3] : c[1];
-        o[2] = solid ? t[4] : c[2];
-        o[3] = solid ? t[1] : c[3];
-        o[4] = solid ? t[2] : c[4];
-        o[5] = solid ? t[7] : c[5];
-        o[6] = solid ? t[8] : c[6];
-        o[7] = solid ? t[5] : c[7];
-        o[8] = solid ? t[6] : c[8];
-        float f[Q]; // what is stored / sent: accelerated on the driven row
+        // ---- collision / bounce-back without |u|; f = what is stored / sent: accelerate_flow() of the next step applied
+        // on the driven row
+        float o[Q][CPT], speed[CPT];
+        bool speed_done;
+        if constexpr (CPT == 1) {
+            // one cell: the scalar collision without its |u| half (formed from o after the packets have left)
+            float tc[Q], c[Q];
 #pragma unroll
-        for (int k = 0; k < Q; k++) f[k] = o[k];
-        if (on_accel_row && (a.first_step + s != a.last_step)) accelerate_cell(f, solid, a.w1a, a.w2a);
+            for (int k = 0; k < Q; k++) tc[k] = t[k][0];
+            collide_cell<STRICT, false>(tc, a.omega, c);
+            constexpr int mirror[Q] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+            const bool solid = obits & 1u;
+#pragma unroll
+            for (int k = 0; k < Q; k++) o[k][0] = solid ? tc[mirror[k]] : c[k];
+            speed_done = false;
+        } else {
+            speed_done = cells_relax<STRICT, CPT, VERT>(t, obits, a.omega, o, speed);
+        }
+        float f[Q][CPT];
+#pragma unroll
+        for (int k = 0; k < Q; k++)
+#pragma unroll
+            for (int j = 0; j < CPT; j++) f[k][j] = o[k][j];
+        if (on_accel_row && (a.first_step + s != a.last_step)) {
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                float fc[Q];
+#pragma unroll
+                for (int k = 0; k < Q; k++) fc[k] = f[k][j];
+                accelerate_cell(fc, (obits >> j) & 1u, a.w1a, a.w2a);
+#pragma unroll
+                for (int k = 0; k < Q; k++) f[k][j] = fc[k];
+            }
+        }
 
         float* xs = xch + static_cast<size_t>(par) * 6 * nthr;
         if (!last) {
-            // ---- sideways exchange inside the row
-            xs[0 * nthr + tid] = f[1], xs[1 * nthr + tid] = f[3], xs[2 * nthr + tid] = f[5];
-            xs[3 * nthr + tid] = f[6], xs[4 * nthr + tid] = f[7], xs[5 * nthr + tid] = f[8];
+            // ---- what leaves my cells sideways: f1, f5, f8 of the last cell go east, f3, f6, f7 of the first go west
+            xs[0 * nthr + tid] = f[1][CPT - 1], xs[1 * nthr + tid] = f[3][0], xs[2 * nthr + tid] = f[5][CPT - 1];
+            xs[3 * nthr + tid] = f[6][0], xs[4 * nthr + tid] = f[7][0], xs[5 * nthr + tid] = f[8][CPT - 1];
         } else if (valid) {
-            const size_t off = static_cast<size_t>(y) * pitch + x;
-#pragma unroll
-            for (int k = 0; k < Q; k++) out[k * a.pf + off] = f[k];
+            float* dst = out + static_cast<size_t>(y) * pitch + x0;
+            store_cells<CPT>(dst, a.pf, f);
         }
         __syncthreads();
         const unsigned flag = a.flag_base + static_cast<unsigned>(s) + 1u;
-        float t1 = 0.f, t3 = 0.f;
+        float f1w = 0.f, f3e = 0.f;
         if (!last) {
-            t1 = xs[0 * nthr + xw], t3 = xs[1 * nthr + xe];
-            const float p5 = xs[2 * nthr + xw], p6 = xs[3 * nthr + xe], p7 = xs[4 * nthr + xe], p8 = xs[5 * nthr + xw];
+            f1w = xs[0 * nthr + tw], f3e = xs[1 * nthr + te];
+            const float f5w = xs[2 * nthr + tw], f6e = xs[3 * nthr + te], f7e = xs[4 * nthr + te], f8w = xs[5 * nthr + tw];
             if (valid) {
-                st_packet(my_north + par * rows_pitch, f[2], p5, p6, flag);
-                st_packet(my_south + par * rows_pitch, f[4], p7, p8, flag);
+                uint4* pn = my_north + par * stride_n;
+                uint4* ps = my_south + par * stride_s;
+#pragma unroll
+                for (int j = 0; j < CPT; j++) {
+                    const float a5 = (j > 0) ? f[5][j > 0 ? j - 1 : 0] : f5w, a6 = (j + 1 < CPT) ? f[6][j + 1 < CPT ? j + 1 : 0] : f6e;
+                    const float a7 = (j + 1 < CPT) ? f[7][j + 1 < CPT ? j + 1 : 0] : f7e, a8 = (j > 0) ? f[8][j > 0 ? j - 1 : 0] : f8w;
+                    if (peer_n) st_packet<true>(pn + j, f[2][j], a5, a6, flag);
+                    else st_packet<false>(pn + j, f[2][j], a5, a6, flag);
+                    if (peer_s) st_packet<true>(ps + j, f[4][j], a7, a8, flag);
+                    else st_packet<false>(ps + j, f[4][j], a7, a8, flag);
+                }
             }
         }
         // ---- the |u| sums of the previous step are complete in shared memory (this step's barrier): three threads
@@ -167,9 +276,17 @@ __global__ void __launch_bounds__(1024) step_ll_kernel(const LLArgs a)
         }
         // ---- |u| of the collided state, while the packets travel
         {
-            const float sp = speed_cell<STRICT>(c);
+            if constexpr (CPT == 1) {
+                float c[Q];
+#pragma unroll
+                for (int k = 0; k < Q; k++) c[k] = o[k][0];
+                speed[0] = STRICT ? speed_strict(c) : speed_fast_guarded(c); // an obstacle cell's value is not counted
+            } else {
+                if (!speed_done) cells_speed<STRICT, CPT, VERT>(o, obits, speed);
+            }
             SpeedAcc acc = {0u, 0u, 0u};
-            acc_speed(acc, sp, valid && !solid);
+#pragma unroll
+            for (int j = 0; j < CPT; j++) acc_speed(acc, speed[j], valid && !((obits >> j) & 1u));
             const unsigned lo = __reduce_add_sync(0xffffffffu, acc.lo);
             const unsigned hi = __reduce_add_sync(0xffffffffu, acc.hi);
             const unsigned nbad = __reduce_add_sync(0xffffffffu, acc.bad);
@@ -179,30 +296,18 @@ __global__ void __launch_bounds__(1024) step_ll_kernel(const LLArgs a)
             }
         }
         if (last) break;
-        // ---- wait for the two packets of this step from the rows below and above
+        // ---- wait for this step's packets from the rows below and above, assemble the next step's gather
         {
-            const uint4* ps = from_south + par * rows_pitch;
-            const uint4* pn = from_north + par * rows_pitch;
-            uint4 S = ld_packet(ps), N = ld_packet(pn);
-            bool ok_s = (S.w == flag), ok_n = (N.w == flag);
-            if (!(ok_s && ok_n) && !lost) {
-                const unsigned long long t0 = globaltimer_ns();
-                unsigned spins = 0;
-                while (true) {
-                    if (!ok_s) S = ld_packet(ps), ok_s = (S.w == flag);
-                    if (!ok_n) N = ld_packet(pn), ok_n = (N.w == flag);
-                    if (ok_s && ok_n) break;
-                    if ((++spins & 255u) == 0u &&
-                        (globaltimer_ns() - t0 > a.timeout_ns || *reinterpret_cast<volatile const int*>(a.error))) {
-                        atomicExch(a.error, 1);
-                        lost = true; // the run is lost: finish without waiting any more
-                        break;
-                    }
-                }
+            uint4 S[CPT], N[CPT];
+            wait_packets<CPT, HALO>(from_south + par * stride_s, from_north + par * stride_n, true, true, peer_s, peer_n, flag, S, N, lost, a);
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                t[0][j] = f[0][j];
+                t[1][j] = (j > 0) ? f[1][j > 0 ? j - 1 : 0] : f1w;
+                t[3][j] = (j + 1 < CPT) ? f[3][j + 1 < CPT ? j + 1 : 0] : f3e;
+                t[2][j] = __uint_as_float(S[j].x), t[5][j] = __uint_as_float(S[j].y), t[6][j] = __uint_as_float(S[j].z);
+                t[4][j] = __uint_as_float(N[j].x), t[7][j] = __uint_as_float(N[j].y), t[8][j] = __uint_as_float(N[j].z);
             }
-            t[0] = f[0], t[1] = t1, t[3] = t3;
-            t[2] = __uint_as_float(S.x), t[5] = __uint_as_float(S.y), t[6] = __uint_as_float(S.z);
-            t[4] = __uint_as_float(N.x), t[7] = __uint_as_float(N.y), t[8] = __uint_as_float(N.z);
         }
     }
     // the last step's sums
@@ -212,6 +317,32 @@ __global__ void __launch_bounds__(1024) step_ll_kernel(const LLArgs a)
         unsigned long long v = 0ull;
         for (int w = 0; w < nwarps; w++) v += pp[w * 4 + tid];
         if (v) atomicAdd(a.sums + (static_cast<size_t>(a.nsteps - 1) * a.nslots + (blockIdx.x & (a.nslots - 1))) * SUM_WORDS + tid, v);
+    }
+}
+
+// Row slabs on several GPUs, start of a run: the packets of the CURRENT state of the slab's first and last row go to
+// the neighbouring GPUs (parity slot 1, flag `seed_flag`), exactly what a step would have sent
+struct LLSeedArgs {
+    const float* lat;    // current lattice of the slab
+    size_t pf;
+    uint4* halo_send_s;  // the south neighbour's packet area for what comes from the north (peer memory)
+    uint4* halo_send_n;
+    unsigned seed_flag;
+    int nx, rows, pitch;
+};
+__global__ void ll_seed_kernel(const LLSeedArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= a.nx) return;
+    const int xw = (x == 0) ? a.nx - 1 : x - 1, xe = (x == a.nx - 1) ? 0 : x + 1;
+    const size_t pitch = a.pitch;
+    {   // row 0 -> the last row of the south neighbour pulls f4(x), f7(x+1), f8(x-1) from it
+        const float* r = a.lat;
+        st_packet<true>(a.halo_send_s + pitch + x, __ldcg(r + 4 * a.pf + x), __ldcg(r + 7 * a.pf + xe), __ldcg(r + 8 * a.pf + xw), a.seed_flag);
+    }
+    {   // last row -> the first row of the north neighbour pulls f2(x), f5(x-1), f6(x+1)
+        const float* r = a.lat + static_cast<size_t>(a.rows - 1) * pitch;
+        st_packet<true>(a.halo_send_n + pitch + x, __ldcg(r + 2 * a.pf + x), __ldcg(r + 5 * a.pf + xw), __ldcg(r + 6 * a.pf + xe), a.seed_flag);
     }
 }
 

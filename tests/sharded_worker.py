@@ -23,11 +23,13 @@ def main():
     from lbm_asynchronous_b200.sharded import ShardedLattice
 
     gin = os.path.join(ROOT, "tests", "golden", "inputs")
-    p = orc.read_params(os.path.join(gin, "input_1024x1024.params"))
-    obst = orc.read_obstacles(os.path.join(gin, "obstacles_1024x1024.dat"), p.nx, p.ny)
+    grid = sys.argv[2] if len(sys.argv) > 2 else "1024x1024"
+    kernel = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    p = orc.read_params(os.path.join(gin, f"input_{grid}.params"))
+    obst = orc.read_obstacles(os.path.join(gin, f"obstacles_{grid}.dat"), p.nx, p.ny)
     iters = 700
     param = make_param(p.nx, p.ny, iters, p.reynolds_dim, p.density, p.accel, p.omega)
-    sh = ShardedLattice(param, lambda r0, r1: obst[r0:r1], local)
+    sh = ShardedLattice(param, lambda r0, r1: obst[r0:r1], local, kernel=kernel)
     sh.run(300)
     av1 = sh.av_vels()
     sh.run(400)

@@ -71,6 +71,52 @@ def test_resident_step_loop_across_gpus(ngpu, pkg, orc):
         assert launches < 200  # a handful of cooperative launches, not one per step
 
 
+@pytest.mark.parametrize("kernel", [401, 404])
+def test_packet_kernel_across_gpus(ngpu, pkg, orc, kernel):
+    """step_ll_kernel on every GPU at once: rows inside a slab exchange packets through L2, the slabs' boundary
+    rows through each other's memory over NVLink (st / ld.relaxed.sys.b128), every run seeded with the packets of
+    the current state.  Same bits as one GPU, also over several lbm_run calls, on a shipped case whose periodic wrap
+    crosses the GPU 0 <-> GPU N-1 link and on a random state."""
+    p, obst = load_case(orc, "128x256")
+    with pkg.Lattice(to_param(p), obst, ngpus=1, kernel=201) as lat:
+        lat.run(600)
+        one = (lat.cells(), lat.tot_u_sums()[0])
+    for n in sorted({2, min(4, ngpu)}):
+        with pkg.Lattice(to_param(p), obst, ngpus=n, kernel=kernel) as lat:
+            sums = []
+            for it in (1, 249, 350):
+                lat.run(it)
+                sums.append(lat.tot_u_sums()[0])
+            many = lat.cells()
+            launches = lat.kernel_launches
+        tot = np.concatenate(sums)
+        assert np.array_equal(bits(one[0]), bits(many)), (n, kernel)
+        assert np.array_equal(one[1][:, 0] + (one[1][:, 1] << 24), tot[:, 0] + (tot[:, 1] << 24)), (n, kernel)
+        assert launches < 300  # one cooperative launch (+ seed) per slab and run after the set-up kernels, not one per step
+    from test_gpu_parity import random_case
+
+    p, obst, cells0 = random_case(orc, 256, 96, seed=12)
+    ref_cells, ref_av = orc.run(p, obst, 9, cells=cells0)
+    with pkg.Lattice(to_param(p, 9), obst, ngpus=2, kernel=kernel) as lat:
+        lat.upload(cells0)
+        lat.run(4)
+        lat.run(5)
+        cells = lat.cells()
+    fluid = obst == 0
+    assert np.array_equal(bits(cells[fluid]), bits(ref_cells[fluid]))
+
+
+def test_packet_kernel_one_process_per_gpu(ngpu, built, tmp_path):
+    """The same through the per-process front end (torchrun, packet areas mapped through CUDA IPC)."""
+    out = tmp_path / "result.npz"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29613", os.path.join(ROOT, "tests", "sharded_worker.py"), str(out), "128x256", "404"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = np.load(out)
+    assert bool(res["cells_equal"]) and bool(res["av_equal"])
+
+
 def test_async_halo_mode_drift_is_small(ngpu, pkg, orc):
     """The stale-halo mode (un-waited MPI_Testall): free running, so no bit-exact expectation and no
     reference fixture (parity unpinned).  Its drift against the synchronous run is

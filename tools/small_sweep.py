@@ -37,7 +37,8 @@ def main():
             arith = parts[2] if len(parts) > 2 else "strict"
             os.environ["LBM_CL_SYNC"] = sync
             try:
-                with pkg.Lattice(make_param(p.nx, p.ny, steps, p.reynolds_dim, p.density, p.accel, p.omega), obst, kernel=kernel, arith=arith) as lat:
+                with pkg.Lattice(make_param(p.nx, p.ny, steps, p.reynolds_dim, p.density, p.accel, p.omega), obst, kernel=kernel, arith=arith,
+                                 ngpus=int(os.environ.get("LBM_SWEEP_GPUS", "1"))) as lat:
                     lat.run(steps)
                     ms = lat.last_run_ms()
                     pr = lat.pressure()
@@ -51,7 +52,7 @@ def main():
                     else:
                         same = "state %s sums %s" % ("identical" if np.array_equal(pr.view(np.uint32), ref[0].view(np.uint32)) else "DIFFERS",
                                                      "identical" if np.array_equal(tot, ref[1]) else "DIFFER")
-                print(f"{grid} steps={steps} kernel={kernel} sync={sync} {arith}: {ms / steps * 1e3:7.3f} us/step "
+                print(f"{grid} gpus={os.environ.get('LBM_SWEEP_GPUS', '1')} steps={steps} kernel={kernel} sync={sync} {arith}: {ms / steps * 1e3:7.3f} us/step "
                       f"{p.nx * p.ny * steps / ms / 1e6:7.2f} GLUPS {same}", flush=True)
             except Exception as ex:
                 print(f"{grid} kernel={kernel} sync={sync} {arith}: FAILED {ex}", flush=True)
