@@ -1,11 +1,8 @@
 #!/bin/bash
 # scratch job script for gpurun (rewritten per call)
 mkdir -p gpurun_out
-export LBM_HALO_TIMEOUT_MS=5000
-rm -f gpurun_out/ll_multi_sweep.txt
-LBM_SWEEP_GPUS=1 timeout 300 python tools/small_sweep.py 0 1024x1024 0 >> gpurun_out/ll_multi_sweep.txt 2>&1
-LBM_SWEEP_GPUS=4 timeout 300 python tools/small_sweep.py 0 1024x1024 0 404 11041 204 404::fast 11041::fast >> gpurun_out/ll_multi_sweep.txt 2>&1
-LBM_SWEEP_GPUS=2 timeout 300 python tools/small_sweep.py 0 1024x1024 0 11041 204 >> gpurun_out/ll_multi_sweep.txt 2>&1
-LBM_SWEEP_GPUS=2 timeout 300 python tools/small_sweep.py 0 128x128,128x256,256x256 0 404 11041 201 >> gpurun_out/ll_multi_sweep.txt 2>&1
-LBM_SWEEP_GPUS=4 timeout 300 python tools/small_sweep.py 0 256x256 0 404 11041 >> gpurun_out/ll_multi_sweep.txt 2>&1
-cat gpurun_out/ll_multi_sweep.txt
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q > gpurun_out/r02d_gputest_multi_4gpu.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/r02d_gputest_multi_4gpu.txt
+tail -n 4 gpurun_out/r02d_gputest_multi_4gpu.txt
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --steps 100 --warmup 10 > gpurun_out/r02d_bench_n4.json 2> gpurun_out/r02d_bench_n4.err; echo "bench rc=$?"
+timeout 20 python tools/bench_line.py gpurun_out/r02d_bench_n4.json < /dev/null
+tail -n 3 gpurun_out/r02d_bench_n4.err
