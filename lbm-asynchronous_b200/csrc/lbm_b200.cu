@@ -331,6 +331,7 @@ constexpr long long LL4_MAX_CELLS = 300000; // up to 1024 x 256 (a quarter of th
 constexpr int LL_SLOTS = 8;               // slots of the per-step sums (one RED per CTA, step and word)
 constexpr long long CLUSTER_MAX_CELLS = 32768; // 128 x 256: above, 16 SMs have more arithmetic than the whole GPU has latency
 constexpr int CLUSTER_MAX_CTAS = 16;
+constexpr long long LOOP_HALO_MAX_CELLS = 600000; // slabs on several GPUs: half of the shipped 1024 x 1024 case
 constexpr long long LOOP_MAX_CELLS = 1400000; // 2 x 36 B x cells <= ~100 MB of the 126 MB L2
 constexpr long long LOOP_VEC4_CELLS = 70000;  // up to 256 x 256: one cell per thread (<= 512 CTAs of 128 threads) beats four;
                                               // above, the one-counter grid barrier gets too slow for that many CTAs
@@ -467,10 +468,12 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
     s.use_loop = false;
     const int total_slabs = L->per_process ? L->nranks : L->nslabs;
     const long long nominal_cells = static_cast<long long>(L->p.nx) * ((L->p.ny + total_slabs - 1) / total_slabs);
-    // default: single slab only -- across GPUs the resident kernels measured no better than the graph path
-    // (profiles/r01_small_grids.md); kernel codes 200/201/204 ask for it explicitly
+    // default: single slabs, and synchronous slabs of up to LOOP_HALO_MAX_CELLS cells on GPUs of their own that
+    // step_ll_kernel does not take (the shipped 1024 x 1024 on 2 GPUs: 11.1 us per step against 13.6 from the step
+    // graphs, profiles/r02_small_grids.md); kernel codes 200/201/204 ask for it explicitly
     if (k.loop && L->opt.use_graph && !L->interleaved &&
-        ((L->opt.kernel >= 200 && L->opt.kernel <= 204) || (total_slabs == 1 && nominal_cells <= LOOP_MAX_CELLS))) {
+        ((L->opt.kernel >= 200 && L->opt.kernel <= 204) || (total_slabs == 1 && nominal_cells <= LOOP_MAX_CELLS) ||
+         (total_slabs > 1 && L->opt.halo_mode == LBM_HALO_SYNC && L->opt.halo_lag == 0 && nominal_cells <= LOOP_HALO_MAX_CELLS))) {
         bool v4 = k.vec4 && nominal_cells >= LOOP_VEC4_CELLS;
         if (L->opt.kernel == 201) v4 = false;
         if (L->opt.kernel == 204) v4 = k.vec4;
