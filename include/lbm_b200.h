@@ -74,9 +74,13 @@ typedef struct {
     int halo_mode;   /* LBM_HALO_*             default LBM_HALO_SYNC */
     int halo_lag;    /* LBM_HALO_SYNC only: boundary rows at step t use the neighbour row of step
                         t-halo_lag (even, >= 0; 0 = exact).  The deterministic stale-halo mode. */
-    int use_graph;   /* 1: keep the step loop on the device (default): one cooperative launch per run for grids
-                        that live in L2, CUDA graphs of 32 steps otherwise; 0: one plain launch per step */
-    int kernel;      /* kernel variant, 0 = library default; for tuning/bench only */
+    int use_graph;   /* 1: keep the step loop on the device (default): one cooperative launch per run for small
+                        grids and slabs (cells in registers, rows exchanging flagged packets -- also between GPUs) and
+                        for grids that live in L2, CUDA graphs of 32 steps otherwise; 0: one plain launch per step */
+    int kernel;      /* kernel variant, 0 = library default; for tuning/bench only.  The codes are listed above
+                        choose_kernel() in csrc/lbm_b200.cu and in DESIGN.md 3 (400/401/404 step_ll_kernel, 500/5BM
+                        step_band_kernel, 3000/3CVM step_cluster_kernel, 200/201/204 step_loop_kernel, 1TTSM
+                        step_tma_kernel, 2RRSNM step2_kernel, HM step_vec4_kernel, 99 step_scalar_kernel) */
     int block;       /* threads per CTA, 0 = default */
 } lbm_options_t;
 

@@ -1326,12 +1326,15 @@ int push_boundary_rows(lbm_lattice* L, Slab& s)
 }
 
 // what both ends of a halo link must agree on, packed into the handle: arithmetic flavour, halo mode and lag,
-// and whether the lattice advances in pairs of steps (the epoch sequence differs)
+// whether the lattice advances in pairs of steps (the epoch sequence differs), which resident kernel it runs, and the
+// tuning options that change how many CTAs signal a halo row (opt.block, opt.kernel)
 int32_t halo_config_word(const lbm_lattice* L)
 {
     return static_cast<int32_t>((L->opt.arith & 0xf) | ((L->opt.halo_mode & 0xf) << 4) | ((L->opt.halo_lag & 0xff) << 8) |
                                 ((L->slabs[0].use_f2 ? 1 : 0) << 16) | ((L->slabs[0].use_loop ? 1 : 0) << 17) |
-                                ((L->slabs[0].use_ll ? 1 + L->slabs[0].ll_var : 0) << 18));
+                                ((L->slabs[0].use_ll ? 1 + L->slabs[0].ll_var : 0) << 18) |
+                                // CTA shape and kernel code decide how many CTAs signal a halo row: both ends must agree
+                                (((L->opt.block / 128) & 0x7) << 20) | ((static_cast<unsigned>(L->opt.kernel) * 2654435761u >> 24) << 23 & 0x7f800000));
 }
 
 // the halo protocol stores and adds into the neighbour device's memory from inside kernels: peer access is not
