@@ -1733,7 +1733,7 @@ int lbm_run(lbm_lattice_t* L, int iters)
     if (cluster || ll || band) all_loop = true; // no graphs, no per-step launches
     if (band && !L->slabs[0].band_flags) {
         CU(cudaSetDevice(L->slabs[0].device));
-        CU(cudaMalloc(&L->slabs[0].band_flags, static_cast<size_t>(L->slabs[0].band_grid) * 32 * sizeof(unsigned)));
+        CU(cudaMalloc(&L->slabs[0].band_flags, (static_cast<size_t>(L->slabs[0].band_grid) * 32 + 1 + 2 * 1024) * sizeof(unsigned)));
     }
     if (ll) {
         f2 = false;
@@ -1842,7 +1842,13 @@ int lbm_run(lbm_lattice_t* L, int iters)
         a.nx = L->p.nx, a.nxv = L->p.nx / 4, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
         a.accel_row = s.accel_row;
         a.omega = L->p.omega, a.w1a = L->w1a, a.w2a = L->w2a;
-        CU(cudaMemsetAsync(s.band_flags, 0, static_cast<size_t>(s.band_grid) * 32 * sizeof(unsigned), s.stream));
+        // full occupancy: the rows are dealt out per SM (the CTAs find their SM themselves)
+        const bool sm_aware = static_cast<long long>(s.band_grid) == static_cast<long long>(L->band_resident) * L->sm_count &&
+                              !(getenv("LBM_BAND_SM") && atoi(getenv("LBM_BAND_SM")) == 0);
+        a.per_sm = sm_aware ? L->band_resident : 0;
+        a.nsm = L->sm_count;
+        a.sm_table = s.band_flags + static_cast<size_t>(s.band_grid) * 32;
+        CU(cudaMemsetAsync(s.band_flags, 0, (static_cast<size_t>(s.band_grid) * 32 + 1 + 2 * 1024) * sizeof(unsigned), s.stream));
         void* kp[1] = {&a};
         CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(L->band_kernel), dim3(s.band_grid), dim3(static_cast<unsigned>(L->band_block)),
                                        kp, 0, s.stream));

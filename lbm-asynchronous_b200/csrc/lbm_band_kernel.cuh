@@ -38,6 +38,10 @@ struct BandArgs {
     int nx, nxv, rows, pitch, opitch;
     int accel_row;
     float omega, w1a, w2a;
+    // SM-aware band sizes (per_sm > 0: the grid is exactly per_sm CTAs on each of nsm SMs): CTAs find out which SM they
+    // run on and the rows are dealt out per SM first, so that every SM has the same number of rows to within one
+    int per_sm, nsm;
+    unsigned* sm_table;  // [1 + 2 * 1024] zeroed before the launch: dense SM counter, per-%smid CTA counter, per-%smid dense id + 1
 };
 
 __device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v)
@@ -50,10 +54,37 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_band_kernel(const BandArgs a
 {
     __shared__ unsigned long long s_part[2][BLOCK / 32][3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = gridDim.x, b = blockIdx.x;
-    const int q = a.rows / G, rem = a.rows % G;
-    const int r0 = b * q + min(b, rem);
-    const int nr = q + (b < rem ? 1 : 0); // >= 1: the host launches at most `rows` CTAs
+    const int G = gridDim.x;
+    int b = blockIdx.x, r0, nr;
+    if (a.per_sm > 0) {
+        // which SM am I on, and the how-manieth CTA there?  (cooperative launch at full occupancy: exactly per_sm each)
+        __shared__ int s_b;
+        if (tid == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            smid &= 1023u;
+            const unsigned rank = atomicAdd(a.sm_table + 1 + smid, 1u);
+            unsigned* dense_p = a.sm_table + 1 + 1024 + smid;
+            if (rank == 0) atomicExch(dense_p, atomicAdd(a.sm_table, 1u) + 1u);
+            unsigned dense;
+            while ((dense = ld_acquire_gpu_u32(dense_p)) == 0u) {
+            }
+            s_b = static_cast<int>(dense - 1u) * a.per_sm + static_cast<int>(rank % static_cast<unsigned>(a.per_sm));
+        }
+        __syncthreads();
+        b = s_b;
+        // rows per SM first (balanced to within one), then per CTA of the SM
+        const int sm = b / a.per_sm, k = b - sm * a.per_sm;
+        const int qs = a.rows / a.nsm, rs = a.rows % a.nsm;
+        const int sm_r0 = sm * qs + min(sm, rs), sm_nr = qs + (sm < rs ? 1 : 0);
+        const int qc = sm_nr / a.per_sm, rc = sm_nr % a.per_sm;
+        r0 = sm_r0 + k * qc + min(k, rc);
+        nr = qc + (k < rc ? 1 : 0); // >= 1: the host asks for this only with rows >= 2 * CTAs
+    } else {
+        const int q = a.rows / G, rem = a.rows % G;
+        r0 = b * q + min(b, rem);
+        nr = q + (b < rem ? 1 : 0); // >= 1: the host launches at most `rows` CTAs
+    }
     const unsigned* flag_s = a.flags + static_cast<size_t>((b + G - 1) % G) * 32;
     const unsigned* flag_n = a.flags + static_cast<size_t>((b + 1) % G) * 32;
     unsigned* flag_own = a.flags + static_cast<size_t>(b) * 32;
@@ -134,7 +165,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_band_kernel(const BandArgs a
         if (tid < 3) {
             unsigned long long v = 0ull;
             for (int w = 0; w < BLOCK / 32; w++) v += s_part[s & 1][w][tid];
-            if (v) atomicAdd(a.sums + (static_cast<size_t>(s) * a.nslots + (blockIdx.x & (a.nslots - 1))) * SUM_WORDS + tid, v);
+            if (v) atomicAdd(a.sums + (static_cast<size_t>(s) * a.nslots + (b & (a.nslots - 1))) * SUM_WORDS + tid, v);
         }
     }
 }
