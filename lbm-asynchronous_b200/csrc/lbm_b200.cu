@@ -1733,7 +1733,7 @@ int lbm_run(lbm_lattice_t* L, int iters)
     if (cluster || ll || band) all_loop = true; // no graphs, no per-step launches
     if (band && !L->slabs[0].band_flags) {
         CU(cudaSetDevice(L->slabs[0].device));
-        CU(cudaMalloc(&L->slabs[0].band_flags, (static_cast<size_t>(L->slabs[0].band_grid) * 32 + 1 + 2 * 1024) * sizeof(unsigned)));
+        CU(cudaMalloc(&L->slabs[0].band_flags, (static_cast<size_t>(L->slabs[0].band_grid) * 32 + 1 + 2 * 1024 + 2) * sizeof(unsigned)));
     }
     if (ll) {
         f2 = false;
@@ -1848,7 +1848,7 @@ int lbm_run(lbm_lattice_t* L, int iters)
         a.per_sm = sm_aware ? L->band_resident : 0;
         a.nsm = L->sm_count;
         a.sm_table = s.band_flags + static_cast<size_t>(s.band_grid) * 32;
-        CU(cudaMemsetAsync(s.band_flags, 0, (static_cast<size_t>(s.band_grid) * 32 + 1 + 2 * 1024) * sizeof(unsigned), s.stream));
+        CU(cudaMemsetAsync(s.band_flags, 0, (static_cast<size_t>(s.band_grid) * 32 + 1 + 2 * 1024 + 2) * sizeof(unsigned), s.stream));
         void* kp[1] = {&a};
         CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(L->band_kernel), dim3(s.band_grid), dim3(static_cast<unsigned>(L->band_block)),
                                        kp, 0, s.stream));

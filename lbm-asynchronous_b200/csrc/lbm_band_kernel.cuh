@@ -41,7 +41,8 @@ struct BandArgs {
     // SM-aware band sizes (per_sm > 0: the grid is exactly per_sm CTAs on each of nsm SMs): CTAs find out which SM they
     // run on and the rows are dealt out per SM first, so that every SM has the same number of rows to within one
     int per_sm, nsm;
-    unsigned* sm_table;  // [1 + 2 * 1024] zeroed before the launch: dense SM counter, per-%smid CTA counter, per-%smid dense id + 1
+    unsigned* sm_table;  // [1 + 2 * 1024 + 2] zeroed before the launch: dense SM counter, per-%smid CTA counter, per-%smid dense
+                         // id + 1, CTAs that have a ticket, placement-irregular flag
 };
 
 __device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v)
@@ -69,18 +70,30 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_band_kernel(const BandArgs a
             unsigned dense;
             while ((dense = ld_acquire_gpu_u32(dense_p)) == 0u) {
             }
-            s_b = static_cast<int>(dense - 1u) * a.per_sm + static_cast<int>(rank % static_cast<unsigned>(a.per_sm));
+            // one grid-wide rendezvous per launch: if the placement is not what a full-occupancy cooperative launch
+            // gives (more CTAs on an SM than expected, fewer SMs in use), everybody falls back to bands by blockIdx
+            unsigned* arrived = a.sm_table + 1 + 2 * 1024, *irregular = arrived + 1;
+            if (rank >= static_cast<unsigned>(a.per_sm)) atomicExch(irregular, 1u);
+            __threadfence();
+            atomicAdd(arrived, 1u);
+            while (ld_acquire_gpu_u32(arrived) < static_cast<unsigned>(G)) {
+            }
+            const bool bad = ld_acquire_gpu_u32(irregular) != 0u || ld_acquire_gpu_u32(a.sm_table) != static_cast<unsigned>(a.nsm);
+            s_b = bad ? -1 : static_cast<int>(dense - 1u) * a.per_sm + static_cast<int>(rank);
         }
         __syncthreads();
         b = s_b;
+    }
+    if (a.per_sm > 0 && b >= 0) {
         // rows per SM first (balanced to within one), then per CTA of the SM
         const int sm = b / a.per_sm, k = b - sm * a.per_sm;
         const int qs = a.rows / a.nsm, rs = a.rows % a.nsm;
         const int sm_r0 = sm * qs + min(sm, rs), sm_nr = qs + (sm < rs ? 1 : 0);
         const int qc = sm_nr / a.per_sm, rc = sm_nr % a.per_sm;
         r0 = sm_r0 + k * qc + min(k, rc);
-        nr = qc + (k < rc ? 1 : 0); // >= 1: the host asks for this only with rows >= 2 * CTAs
+        nr = qc + (k < rc ? 1 : 0); // >= 1: the host asks for this only with rows >= CTAs
     } else {
+        b = blockIdx.x;
         const int q = a.rows / G, rem = a.rows % G;
         r0 = b * q + min(b, rem);
         nr = q + (b < rem ? 1 : 0); // >= 1: the host launches at most `rows` CTAs
