@@ -110,12 +110,25 @@ template <int N, bool HALO>
 __device__ __forceinline__ void wait_packets(const uint4* ps, const uint4* pn, bool want_s, bool want_n, bool sys_s, bool sys_n, unsigned flag,
                                              uint4 (&S)[N], uint4 (&NN)[N], bool& lost, const LLArgs& a)
 {
+    // first round: straight-line loads, all in flight together (the common case needs no second one with four cells
+    // per thread, one or two with one cell)
+    if (want_s) {
+#pragma unroll
+        for (int j = 0; j < N; j++) S[j] = (HALO && sys_s) ? ld_packet<true>(ps + j) : ld_packet<false>(ps + j);
+    }
+    if (want_n) {
+#pragma unroll
+        for (int j = 0; j < N; j++) NN[j] = (HALO && sys_n) ? ld_packet<true>(pn + j) : ld_packet<false>(pn + j);
+    }
     unsigned pending = 0u;
-    if (want_s) pending |= (1u << N) - 1u;
-    if (want_n) pending |= ((1u << N) - 1u) << N;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        if (want_s && S[j].w != flag) pending |= 1u << j;
+        if (want_n && NN[j].w != flag) pending |= 1u << (N + j);
+    }
     unsigned long long t0 = 0ull;
     unsigned spins = 0;
-    while (true) {
+    while (pending != 0u && !lost) {
 #pragma unroll
         for (int j = 0; j < N; j++) {
             if (pending & (1u << j)) S[j] = (HALO && sys_s) ? ld_packet<true>(ps + j) : ld_packet<false>(ps + j);
@@ -126,14 +139,12 @@ __device__ __forceinline__ void wait_packets(const uint4* ps, const uint4* pn, b
             if ((pending & (1u << j)) && S[j].w == flag) pending &= ~(1u << j);
             if ((pending & (1u << (N + j))) && NN[j].w == flag) pending &= ~(1u << (N + j));
         }
-        if (pending == 0u || lost) break;
         if ((++spins & 255u) == 0u) { // not on the fast path: the clock and the error word cost an L2 round trip
             const unsigned long long now = globaltimer_ns();
             if (t0 == 0ull) t0 = now;
             if (now - t0 > a.timeout_ns || *reinterpret_cast<volatile const int*>(a.error)) {
                 atomicExch(a.error, 1);
                 lost = true;
-                break;
             }
         }
     }
