@@ -136,6 +136,7 @@ struct Slab {
     // whole runs in one cooperative launch of step_band_kernel: a band of rows per CTA, neighbour flags
     bool use_band = false;
     unsigned band_grid = 0;
+    int band_per_sm = 0;            // > 0: band_grid = band_per_sm CTAs on each SM, rows dealt out per SM
     unsigned* band_flags = nullptr; // [band_grid][32]
     // interior rows through step_tma_kernel
     bool use_tma = false;
@@ -331,7 +332,9 @@ constexpr long long LL4_MAX_CELLS = 300000; // up to 1024 x 256 (a quarter of th
 constexpr int LL_SLOTS = 8;               // slots of the per-step sums (one RED per CTA, step and word)
 constexpr long long CLUSTER_MAX_CELLS = 32768; // 128 x 256: above, 16 SMs have more arithmetic than the whole GPU has latency
 constexpr int CLUSTER_MAX_CTAS = 16;
-constexpr long long LOOP_HALO_MAX_CELLS = 600000; // slabs on several GPUs: half of the shipped 1024 x 1024 case
+constexpr int BAND_MIN_PER_SM = 3;                // step_band_kernel across GPUs by default: rows per slab >= 3 x SMs
+constexpr long long LOOP_HALO_MAX_CELLS = 1400000; // slabs on several GPUs: the same bound (2048 x 1024 on 2 GPUs: 15.7 us from
+                                                   // the resident step loop against 24.7 from the step graphs)
 constexpr long long LOOP_MAX_CELLS = 1400000; // 2 x 36 B x cells <= ~100 MB of the 126 MB L2
 constexpr long long LOOP_VEC4_CELLS = 70000;  // up to 256 x 256: one cell per thread (<= 512 CTAs of 128 threads) beats four;
                                               // above, the one-counter grid barrier gets too slow for that many CTAs
@@ -524,23 +527,34 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
         }
         if (ll_asked && !s.use_ll && getenv("LBM_DEBUG")) fprintf(stderr, "[lbm] step_ll_kernel asked for but not applicable\n");
     }
-    // a band of rows per CTA (cooperative launch, neighbour flags)
+    // a band of rows per CTA (cooperative launch, neighbour flags).  Full SMs only: per_sm CTAs on every SM, the rows
+    // dealt out per SM.  With several slabs every slab needs a GPU of its own and every rank must take the same
+    // decision: it is based on the nominal slab height
     s.use_band = false;
-    if (k.band && L->band_kernel && !s.use_ll && k.vec4 && L->opt.use_graph && !L->interleaved && total_slabs == 1 && L->nslabs == 1 &&
-        ((L->opt.kernel >= 500 && L->opt.kernel < 600) || nominal_cells <= LOOP_MAX_CELLS)) {
-        long long g = static_cast<long long>(L->band_resident) * L->sm_count;
-        if (const char* t = getenv("LBM_BAND_GRID")) {
-            const long long v = atoll(t);
-            if (v >= 1 && v < g) g = v;
-        }
-        // default: only where every resident CTA gets a row (1024 x 1024: 13.3 us per step against 13.9 from
-        // step_loop_kernel); with fewer rows than CTA slots the tile walk of step_loop_kernel spreads a row over
-        // several CTAs and wins (profiles/r02_small_grids.md)
+    {
         const bool asked = (L->opt.kernel >= 500 && L->opt.kernel < 600);
-        if (g > s.rows) g = asked ? s.rows : 0;
-        if (g >= 1) {
-            s.use_band = true;
-            s.band_grid = static_cast<unsigned>(g);
+        const int nominal_rows = (L->p.ny + total_slabs - 1) / total_slabs;
+        const bool halo_ok = !uses_halo_cfg(L) || (L->opt.halo_mode == LBM_HALO_SYNC && L->opt.halo_lag == 0);
+        const long long max_cells = (total_slabs == 1) ? LOOP_MAX_CELLS : LOOP_HALO_MAX_CELLS;
+        if (k.band && L->band_kernel && !s.use_ll && k.vec4 && L->opt.use_graph && !L->interleaved && halo_ok && L->sm_count > 0 &&
+            (asked || nominal_cells <= max_cells)) {
+            const int per_nominal = std::min(L->band_resident, nominal_rows / L->sm_count);
+            // default: a single slab only at full occupancy (592 rows on 148 SMs: below, step_loop_kernel's finer tiles
+            // spread a row over several CTAs and win -- 512 x 512: 6.4 us against 5.2); slabs on several GPUs from three
+            // CTAs per SM (444 rows), because the alternative there is the resident step loop with its halo rings and
+            // system-scope fences (profiles/r02_small_grids.md)
+            if (asked || per_nominal >= (total_slabs == 1 ? L->band_resident : BAND_MIN_PER_SM)) {
+                int per_sm = std::min(L->band_resident, s.rows / L->sm_count);
+                long long g = per_sm >= 1 ? static_cast<long long>(per_sm) * L->sm_count : s.rows;
+                if (const char* t = getenv("LBM_BAND_GRID")) {
+                    const long long v = atoll(t);
+                    if (v >= 1 && v <= std::min<long long>(s.rows, static_cast<long long>(L->band_resident) * L->sm_count)) g = v, per_sm = 0;
+                }
+                if (getenv("LBM_BAND_SM") && atoi(getenv("LBM_BAND_SM")) == 0) per_sm = 0;
+                s.use_band = true;
+                s.band_grid = static_cast<unsigned>(g);
+                s.band_per_sm = per_sm >= 1 ? per_sm : 0;
+            }
         }
     }
     s.use_tma = !s.use_loop && k.tma && L->tma_kernel && s.rows >= 3;
@@ -607,6 +621,10 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
                 s.row0, s.row1 - 1, s.device, s.vec4 ? "vec4" : "scalar", s.grid, s.block, s.grid_b, s.use_loop ? 1 : 0, s.loop_vec, s.loop_grid,
                 s.loop_ntiles, s.use_tma ? 1 : 0, L->tma_ty,
                 L->tma_stages, L->tma_minb, L->tma_resident, L->tma_smem, s.tma_grid, s.tma_ntiles);
+    if (getenv("LBM_DEBUG"))
+        fprintf(stderr, "[lbm] slab rows %d..%d dev %d: single-launch kernels: ll %d (variant %d, %d threads), band %d (grid %u, %d per SM), cluster %d\n",
+                s.row0, s.row1 - 1, s.device, s.use_ll ? 1 : 0, s.ll_var, s.ll_block, s.use_band ? 1 : 0, s.band_grid, s.band_per_sm,
+                s.use_cluster ? 1 : 0);
     // spread the per-step global atomics over several addresses when there are many CTAs
     const unsigned ctas = s.use_tma ? std::max(s.tma_grid + s.grid_b, s.f2_grid) : s.grid;
     int slots = 1;
@@ -1102,24 +1120,32 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
             if (!coop) L->loop_kernel[v] = nullptr;
         }
     }
-    if (k.band && k.vec4 && !L->interleaved && !uses_halo_cfg(L) && L->nslabs == 1) {
-        CU(cudaSetDevice(L->slabs[0].device));
-        int sms = 0, coop = 0;
-        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, L->slabs[0].device));
-        CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, L->slabs[0].device));
-        L->sm_count = sms;
+    if (k.band && k.vec4 && !L->interleaved) {
+        const bool halo = uses_halo_cfg(L);
         void (*fn)(BandArgs) = nullptr;
         const int bb = k.band_block, bm = k.band_minb;
-        if (bb == 256 && bm == 2) fn = strict ? step_band_kernel<true, 256, 2, false> : step_band_kernel<false, 256, 2, false>;
-        else if (bb == 128 && bm == 4) fn = strict ? step_band_kernel<true, 128, 4, false> : step_band_kernel<false, 128, 4, false>;
-        else if (bb == 256 && bm == 1) fn = strict ? step_band_kernel<true, 256, 1, true> : step_band_kernel<false, 256, 1, true>;
-        else if (bb == 512 && bm == 1) fn = strict ? step_band_kernel<true, 512, 1, false> : step_band_kernel<false, 512, 1, false>;
-        else return fail(LBM_EINVAL, "no step_band_kernel variant with %d threads and %d CTAs per SM", bb, bm);
-        if (coop) {
-            int resident = 0;
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, reinterpret_cast<const void*>(fn), bb, 0));
-            if (resident >= 1) L->band_kernel = fn, L->band_block = bb, L->band_resident = resident;
+#define LBM_BAND_CASE(B_, M_, V_)                                                                                         \
+    if (bb == B_ && bm == M_)                                                                                             \
+        fn = halo ? (strict ? step_band_kernel<true, B_, M_, V_, true> : step_band_kernel<false, B_, M_, V_, true>)      \
+                  : (strict ? step_band_kernel<true, B_, M_, V_, false> : step_band_kernel<false, B_, M_, V_, false>);
+        LBM_BAND_CASE(256, 2, false)
+        LBM_BAND_CASE(128, 4, false)
+        LBM_BAND_CASE(256, 1, true)
+        LBM_BAND_CASE(512, 1, false)
+#undef LBM_BAND_CASE
+        if (!fn) return fail(LBM_EINVAL, "no step_band_kernel variant with %d threads and %d CTAs per SM", bb, bm);
+        bool ok = true;
+        for (int i = 0; i < L->nslabs; i++) {
+            CU(cudaSetDevice(L->slabs[i].device));
+            int sms = 0, coop = 0, resident = 0;
+            CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, L->slabs[i].device));
+            CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, L->slabs[i].device));
+            if (i == 0 || sms < L->sm_count) L->sm_count = sms;
+            if (coop) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, reinterpret_cast<const void*>(fn), bb, 0));
+            if (i == 0 || resident < L->band_resident) L->band_resident = resident;
+            ok = ok && coop && resident >= 1;
         }
+        if (ok) L->band_kernel = fn, L->band_block = bb;
     }
     if (k.ll && !L->interleaved) {
         const bool halo = uses_halo_cfg(L);
@@ -1334,7 +1360,8 @@ int32_t halo_config_word(const lbm_lattice* L)
                                 ((L->slabs[0].use_f2 ? 1 : 0) << 16) | ((L->slabs[0].use_loop ? 1 : 0) << 17) |
                                 ((L->slabs[0].use_ll ? 1 + L->slabs[0].ll_var : 0) << 18) |
                                 // CTA shape and kernel code decide how many CTAs signal a halo row: both ends must agree
-                                (((L->opt.block / 128) & 0x7) << 20) | ((static_cast<unsigned>(L->opt.kernel) * 2654435761u >> 24) << 23 & 0x7f800000));
+                                (((L->opt.block / 128) & 0x7) << 20) | ((L->slabs[0].use_band ? 1 : 0) << 23) |
+                                ((static_cast<unsigned>(L->opt.kernel) * 2654435761u >> 25) << 24 & 0x7f000000));
 }
 
 // the halo protocol stores and adds into the neighbour device's memory from inside kernels: peer access is not
@@ -1727,13 +1754,21 @@ int lbm_run(lbm_lattice_t* L, int iters)
     bool all_loop = true, f2 = true;
     bool ll = true;
     for (int i = 0; i < L->nslabs; i++) ll = ll && L->slabs[i].use_ll;
-    const bool band = !ll && (L->nslabs == 1 && L->slabs[0].use_band);
+    bool band = !ll;
+    for (int i = 0; i < L->nslabs; i++) band = band && L->slabs[i].use_band;
     const bool cluster = !ll && !band && (L->nslabs == 1 && L->slabs[0].use_cluster);
     for (int i = 0; i < L->nslabs; i++) all_loop = all_loop && L->slabs[i].use_loop, f2 = f2 && L->slabs[i].use_f2;
     if (cluster || ll || band) all_loop = true; // no graphs, no per-step launches
-    if (band && !L->slabs[0].band_flags) {
-        CU(cudaSetDevice(L->slabs[0].device));
-        CU(cudaMalloc(&L->slabs[0].band_flags, (static_cast<size_t>(L->slabs[0].band_grid) * 32 + 1 + 2 * 1024 + 2) * sizeof(unsigned)));
+    if (band) {
+        f2 = false;
+        for (int i = 0; i < L->nslabs; i++) {
+            Slab& s = L->slabs[i];
+            if (s.band_flags) continue;
+            CU(cudaSetDevice(s.device));
+            CU(cudaMalloc(&s.band_flags, (static_cast<size_t>(s.band_grid) * 32 + 1 + 2 * 1024 + 2) * sizeof(unsigned)));
+        }
+        if (uses_halo(L) && static_cast<unsigned long long>(L->ll_flags) + static_cast<unsigned long long>(iters) + 2ull > 0x7fffffffull)
+            return fail(LBM_EINVAL, "packet flags exhausted (2^31 steps on one multi-GPU lattice)");
     }
     if (ll) {
         f2 = false;
@@ -1824,35 +1859,58 @@ int lbm_run(lbm_lattice_t* L, int iters)
     long long passes = 0; // lattice swaps queued
     long long epochs = 0; // halo epochs queued after epoch_base
     if (band) {
-        // every step of this run in ONE cooperative launch of step_band_kernel, a band of rows per CTA
-        Slab& s = L->slabs[0];
-        CU(cudaSetDevice(s.device));
-        BandArgs a;
-        memset(&a, 0, sizeof a);
-        a.lat[0] = s.lat[0], a.lat[1] = s.lat[1];
-        a.pf = plane_floats(L, s);
-        a.obst = s.obst;
-        a.sums = s.sums;
-        a.nslots = s.nslots;
-        a.flags = s.band_flags;
-        a.error = s.error;
-        a.timeout_ns = L->timeout_ns;
-        a.first_step = first, a.nsteps = iters, a.last_step = first + iters - 1;
-        a.src = parity;
-        a.nx = L->p.nx, a.nxv = L->p.nx / 4, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
-        a.accel_row = s.accel_row;
-        a.omega = L->p.omega, a.w1a = L->w1a, a.w2a = L->w2a;
-        // full occupancy: the rows are dealt out per SM (the CTAs find their SM themselves)
-        const bool sm_aware = static_cast<long long>(s.band_grid) == static_cast<long long>(L->band_resident) * L->sm_count &&
-                              !(getenv("LBM_BAND_SM") && atoi(getenv("LBM_BAND_SM")) == 0);
-        a.per_sm = sm_aware ? L->band_resident : 0;
-        a.nsm = L->sm_count;
-        a.sm_table = s.band_flags + static_cast<size_t>(s.band_grid) * 32;
-        CU(cudaMemsetAsync(s.band_flags, 0, (static_cast<size_t>(s.band_grid) * 32 + 1 + 2 * 1024 + 2) * sizeof(unsigned), s.stream));
-        void* kp[1] = {&a};
-        CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(L->band_kernel), dim3(s.band_grid), dim3(static_cast<unsigned>(L->band_block)),
-                                       kp, 0, s.stream));
-        L->launches++;
+        // every step of this run in ONE cooperative launch of step_band_kernel per slab, a band of rows per CTA; slabs
+        // on different GPUs run at the same time and exchange step_ll_kernel's (unshifted) packets at their boundaries
+        const unsigned flag_base = L->ll_flags + 1u;
+        if (uses_halo(L))
+            for (int i = 0; i < L->nslabs; i++) {
+                Slab& s = L->slabs[i];
+                CU(cudaSetDevice(s.device));
+                LLSeedArgs sa;
+                sa.lat = s.lat[parity];
+                sa.pf = plane_floats(L, s);
+                sa.halo_send_s = s.peer_ll_s, sa.halo_send_n = s.peer_ll_n;
+                sa.seed_flag = flag_base;
+                sa.nx = L->p.nx, sa.rows = s.rows, sa.pitch = L->pitch;
+                sa.unshifted = 1;
+                ll_seed_kernel<<<(L->p.nx + 127) / 128, 128, 0, s.stream>>>(sa);
+                L->launches++;
+                CU(cudaGetLastError());
+            }
+        for (int i = 0; i < L->nslabs; i++) {
+            Slab& s = L->slabs[i];
+            CU(cudaSetDevice(s.device));
+            BandArgs a;
+            memset(&a, 0, sizeof a);
+            a.lat[0] = s.lat[0], a.lat[1] = s.lat[1];
+            a.pf = plane_floats(L, s);
+            a.obst = s.obst;
+            a.sums = s.sums;
+            a.nslots = s.nslots;
+            a.flags = s.band_flags;
+            a.error = s.error;
+            a.timeout_ns = L->timeout_ns;
+            a.first_step = first, a.nsteps = iters, a.last_step = first + iters - 1;
+            a.src = parity;
+            a.nx = L->p.nx, a.nxv = L->p.nx / 4, a.rows = s.rows, a.pitch = L->pitch, a.opitch = L->opitch;
+            a.accel_row = s.accel_row;
+            a.omega = L->p.omega, a.w1a = L->w1a, a.w2a = L->w2a;
+            if (uses_halo(L)) {
+                a.halo_recv_s = s.ll_recv_s, a.halo_recv_n = s.ll_recv_n;
+                a.halo_send_s = s.peer_ll_s, a.halo_send_n = s.peer_ll_n;
+            }
+            a.flag_base = flag_base;
+            // full SMs: the rows are dealt out per SM (the CTAs find their SM themselves)
+            a.per_sm = s.band_per_sm;
+            a.nsm = L->sm_count;
+            a.sm_table = s.band_flags + static_cast<size_t>(s.band_grid) * 32;
+            CU(cudaMemsetAsync(s.band_flags, 0, (static_cast<size_t>(s.band_grid) * 32 + 1 + 2 * 1024 + 2) * sizeof(unsigned), s.stream));
+            void* kp[1] = {&a};
+            CU(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(L->band_kernel), dim3(s.band_grid),
+                                           dim3(static_cast<unsigned>(L->band_block)), kp, 0, s.stream));
+            L->launches++;
+        }
+        if (uses_halo(L)) L->ll_flags += static_cast<unsigned>(iters) + 1u;
         done = iters;
         passes = iters;
         epochs = iters;
@@ -1870,6 +1928,7 @@ int lbm_run(lbm_lattice_t* L, int iters)
                 sa.halo_send_s = s.peer_ll_s, sa.halo_send_n = s.peer_ll_n;
                 sa.seed_flag = seed_flag;
                 sa.nx = L->p.nx, sa.rows = s.rows, sa.pitch = L->pitch;
+                sa.unshifted = 0;
                 ll_seed_kernel<<<(L->p.nx + 127) / 128, 128, 0, s.stream>>>(sa);
                 L->launches++;
                 CU(cudaGetLastError());

@@ -19,7 +19,7 @@
 // Replaces the timestep loop of SerialCode/d2q9-bgk.c:187-194 for single-GPU grids of up to LOOP_MAX_CELLS cells.
 #pragma once
 
-#include "lbm_kernels.cuh"
+#include "lbm_ll_kernel.cuh" // st_packet / ld_packet / ll_seed_kernel: the packets that cross a GPU boundary
 
 namespace lbm {
 
@@ -38,6 +38,16 @@ struct BandArgs {
     int nx, nxv, rows, pitch, opitch;
     int accel_row;
     float omega, w1a, w2a;
+    // row slabs on several GPUs (HALO): the slab's first / last row exchange step_ll_kernel's UNSHIFTED packets with the
+    // neighbouring GPUs ({f2, f5, f6} / {f4, f7, f8} of one cell + flag, st / ld.relaxed.sys.b128 into / out of the packet
+    // areas [2][pitch] of the halo blocks; the consumer reads the packets of the cells west and east of its own as well).
+    // Step s consumes flag_base + s from slot (s + 1) & 1 (s = 0: what ll_seed_kernel sent) and produces flag_base + s + 1
+    // in slot s & 1.
+    const uint4* halo_recv_s;
+    const uint4* halo_recv_n;
+    uint4* halo_send_s;
+    uint4* halo_send_n;
+    unsigned flag_base;
     // SM-aware band sizes (per_sm > 0: the grid is exactly per_sm CTAs on each of nsm SMs): CTAs find out which SM they
     // run on and the rows are dealt out per SM first, so that every SM has the same number of rows to within one
     int per_sm, nsm;
@@ -50,7 +60,7 @@ __device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <bool STRICT, int BLOCK, int MINB, bool VERT>
+template <bool STRICT, int BLOCK, int MINB, bool VERT, bool HALO>
 __global__ void __launch_bounds__(BLOCK, MINB) step_band_kernel(const BandArgs a)
 {
     __shared__ unsigned long long s_part[2][BLOCK / 32][3];
@@ -103,7 +113,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_band_kernel(const BandArgs a
     unsigned* flag_own = a.flags + static_cast<size_t>(b) * 32;
     const size_t pitch = a.pitch;
     const HaloCfg h = HaloCfg{}; // single slab: periodic in y inside the lattice
-    bool lost = false;
+    bool lost = false; // a wait gave up: the run is lost, nobody waits any more
 
     for (int s = 0; s < a.nsteps; s++) {
         const float* in = a.lat[(a.src + s) & 1];
@@ -147,11 +157,60 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_band_kernel(const BandArgs a
                 const uint32_t oword = __ldg(a.obst + static_cast<size_t>(y) * a.opitch + (c >> 3));
                 float t[Q][4];
                 pull4<3>(rows, c, a.nxv, a.nx, lane, tid, BLOCK, t); // through L2: the source changes every step
+                if (HALO && (y == 0 || y == a.rows - 1)) {
+                    // what crosses the GPU boundary comes out of the neighbour's packets (the periodic wrap inside the
+                    // slab that pull4 just read for those planes is not the neighbour row)
+                    const int x0 = 4 * c;
+                    const int off[6] = {(x0 == 0) ? a.nx - 1 : x0 - 1, x0, x0 + 1, x0 + 2, x0 + 3, (x0 + 4 == a.nx) ? 0 : x0 + 4};
+                    const unsigned want = a.flag_base + static_cast<unsigned>(s);
+                    const size_t slot = static_cast<size_t>((s + 1) & 1) * pitch;
+#pragma unroll
+                    for (int side = 0; side < 2; side++) {
+                        if (side == 0 ? (y != 0) : (y != a.rows - 1)) continue;
+                        const uint4* src = (side == 0 ? a.halo_recv_s : a.halo_recv_n) + slot;
+                        uint4 P[6];
+                        unsigned pending = 0x3fu, spins = 0;
+                        unsigned long long t0 = 0ull;
+                        while (pending != 0u && !lost) {
+#pragma unroll
+                            for (int i = 0; i < 6; i++)
+                                if (pending & (1u << i)) P[i] = ld_packet<true>(src + off[i]);
+#pragma unroll
+                            for (int i = 0; i < 6; i++)
+                                if ((pending & (1u << i)) && P[i].w == want) pending &= ~(1u << i);
+                            if (pending != 0u && (++spins & 255u) == 0u) {
+                                const unsigned long long now = globaltimer_ns();
+                                if (t0 == 0ull) t0 = now;
+                                if (now - t0 > a.timeout_ns || *reinterpret_cast<volatile const int*>(a.error)) {
+                                    atomicExch(a.error, 1);
+                                    lost = true;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (side == 0) {
+                                t[2][j] = __uint_as_float(P[1 + j].x), t[5][j] = __uint_as_float(P[j].y), t[6][j] = __uint_as_float(P[2 + j].z);
+                            } else {
+                                t[4][j] = __uint_as_float(P[1 + j].x), t[7][j] = __uint_as_float(P[2 + j].y), t[8][j] = __uint_as_float(P[j].z);
+                            }
+                        }
+                    }
+                }
                 const uint32_t obits = (oword >> ((c & 7) * 4)) & 0xfu;
                 float o[Q][4];
                 SpeedAcc acc = {0u, 0u, 0u};
                 update4<STRICT, VERT>(t, obits, valid, accel, a.omega, a.w1a, a.w2a, o, acc);
                 if (valid) store4<3>(out, a.pf, roff + 4 * c, o);
+                if (HALO && valid && s + 1 < a.nsteps && (y == 0 || y == a.rows - 1)) {
+                    const unsigned flag = a.flag_base + static_cast<unsigned>(s) + 1u;
+                    const size_t slot = static_cast<size_t>(s & 1) * pitch + 4 * c;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (y == 0) st_packet<true>(a.halo_send_s + slot + j, o[4][j], o[7][j], o[8][j], flag);
+                        if (y == a.rows - 1) st_packet<true>(a.halo_send_n + slot + j, o[2][j], o[5][j], o[6][j], flag);
+                    }
+                }
                 acc_lo += acc.lo, acc_hi += acc.hi, acc_bad += acc.bad;
             }
             if (i == publish_after && s + 1 < a.nsteps) {

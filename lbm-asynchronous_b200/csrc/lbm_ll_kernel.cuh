@@ -340,12 +340,14 @@ struct LLSeedArgs {
     uint4* halo_send_n;
     unsigned seed_flag;
     int nx, rows, pitch;
+    int unshifted;       // 1: a packet holds the populations of its own cell (step_band_kernel shifts at the consumer), 0: already
+                         // shifted for the cell that pulls them (step_ll_kernel)
 };
 __global__ void ll_seed_kernel(const LLSeedArgs a)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= a.nx) return;
-    const int xw = (x == 0) ? a.nx - 1 : x - 1, xe = (x == a.nx - 1) ? 0 : x + 1;
+    const int xw = a.unshifted ? x : ((x == 0) ? a.nx - 1 : x - 1), xe = a.unshifted ? x : ((x == a.nx - 1) ? 0 : x + 1);
     const size_t pitch = a.pitch;
     {   // row 0 -> the last row of the south neighbour pulls f4(x), f7(x+1), f8(x-1) from it
         const float* r = a.lat;

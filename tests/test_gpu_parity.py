@@ -99,7 +99,7 @@ def exact_tot_u(orc, p, obst, cells_before, k):
     (36, 21, 404, 0), (512, 280, 404, 0), (1024, 2, 404, 0),
     # step_band_kernel (a band of rows per CTA, neighbour flags): bands of one row, ragged bands, several passes per row
     (1024, 700, 500, 0), (256, 37, 522, 0), (128, 128, 514, 0), (4096, 200, 521, 0), (12, 9, 500, 0), (64, 64, 522, 0),
-    (640, 300, 514, 0), (128, 2, 500, 0), (256, 5, 541, 0), (2052, 130, 500, 0),
+    (640, 300, 514, 0), (128, 2, 500, 0), (256, 5, 541, 0), (2052, 130, 500, 0), (1024, 460, 0, 0), (512, 600, 0, 0),
 ])
 def test_strict_steps_bit_exact_vs_oracle(gpu, pkg, orc, nx, ny, kernel, block):
     p, obst, cells0 = random_case(orc, nx, ny, seed=nx * 1000 + ny)

@@ -1,9 +1,10 @@
 #!/bin/bash
 # scratch job script for gpurun (rewritten per call)
 mkdir -p gpurun_out
-export LBM_HALO_TIMEOUT_MS=5000
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "strict_steps_bit_exact or av_vels_identical or chunked" > gpurun_out/cl_tests.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/cl_tests.txt
-tail -n 3 gpurun_out/cl_tests.txt
-timeout 300 python tools/small_sweep.py 0 128x128,128x256,256x256 401 404 401::fast > gpurun_out/ll_wait_sweep.txt 2>&1
-timeout 300 python tools/small_sweep.py 20000 1024x256 404 >> gpurun_out/ll_wait_sweep.txt 2>&1
-cat gpurun_out/ll_wait_sweep.txt
+export LBM_HALO_TIMEOUT_MS=8000
+rm -f gpurun_out/band_multi_diag.txt
+LBM_DEBUG=1 LBM_SWEEP_GPUS=2 timeout 300 python tools/small_sweep.py 2000 1024x1024 0 2>&1 | grep -v "graph replay\|dbg" | head -12 >> gpurun_out/band_multi_diag.txt
+LBM_SWEEP_GPUS=1 timeout 300 python tools/small_sweep.py 10000 1024x512 204 514 >> gpurun_out/band_multi_diag.txt 2>&1
+LBM_SWEEP_GPUS=2 timeout 300 python tools/small_sweep.py 10000 1024x1024 514 204 >> gpurun_out/band_multi_diag.txt 2>&1
+LBM_BAND_SM=0 LBM_SWEEP_GPUS=2 timeout 300 python tools/small_sweep.py 10000 1024x1024 514 >> gpurun_out/band_multi_diag.txt 2>&1
+cat gpurun_out/band_multi_diag.txt
