@@ -332,7 +332,7 @@ constexpr long long LL4_MAX_CELLS = 300000; // up to 1024 x 256 (a quarter of th
 constexpr int LL_SLOTS = 8;               // slots of the per-step sums (one RED per CTA, step and word)
 constexpr long long CLUSTER_MAX_CELLS = 32768; // 128 x 256: above, 16 SMs have more arithmetic than the whole GPU has latency
 constexpr int CLUSTER_MAX_CTAS = 16;
-constexpr int BAND_MIN_PER_SM = 3;                // step_band_kernel across GPUs by default: rows per slab >= 3 x SMs
+constexpr int BAND_MIN_PER_SM = 3;                // step_band_kernel by default: rows per slab >= 3 x SMs
 constexpr long long LOOP_HALO_MAX_CELLS = 1400000; // slabs on several GPUs: the same bound (2048 x 1024 on 2 GPUs: 15.7 us from
                                                    // the resident step loop against 24.7 from the step graphs)
 constexpr long long LOOP_MAX_CELLS = 1400000; // 2 x 36 B x cells <= ~100 MB of the 126 MB L2
@@ -539,12 +539,15 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
         if (k.band && L->band_kernel && !s.use_ll && k.vec4 && L->opt.use_graph && !L->interleaved && halo_ok && L->sm_count > 0 &&
             (asked || nominal_cells <= max_cells)) {
             const int per_nominal = std::min(L->band_resident, nominal_rows / L->sm_count);
-            // default: a single slab only at full occupancy (592 rows on 148 SMs: below, step_loop_kernel's finer tiles
-            // spread a row over several CTAs and win -- 512 x 512: 6.4 us against 5.2); slabs on several GPUs from three
-            // CTAs per SM (444 rows), because the alternative there is the resident step loop with its halo rings and
-            // system-scope fences (profiles/r02_small_grids.md)
-            if (asked || per_nominal >= (total_slabs == 1 ? L->band_resident : BAND_MIN_PER_SM)) {
-                int per_sm = std::min(L->band_resident, s.rows / L->sm_count);
+            // default: from three rows per SM (444 rows on 148 SMs); below, step_loop_kernel's finer tiles spread a row
+            // over several CTAs and win (profiles/r02_small_grids.md).  As long as every row can have a CTA of its own
+            // (rows <= resident CTAs) it gets one and the hardware's placement balances the SMs to within one row; with
+            // more rows every SM is full and the rows are dealt out per SM (two rows in one CTA run one after the other:
+            // 512 x 512 with 444 CTAs 6.4 us, with 512 CTAs 5.0 us)
+            // and rows of more than one pass of the CTA: with a single pass per row and step (nx <= 512) the chain
+            // wait - row - fence - flag of a one-row band is all latency (512 x 512: 6.3 us against 5.2)
+            if (asked || (per_nominal >= BAND_MIN_PER_SM && L->p.nx > 4 * L->band_block)) {
+                int per_sm = (static_cast<long long>(s.rows) <= static_cast<long long>(L->band_resident) * L->sm_count) ? 0 : L->band_resident;
                 long long g = per_sm >= 1 ? static_cast<long long>(per_sm) * L->sm_count : s.rows;
                 if (const char* t = getenv("LBM_BAND_GRID")) {
                     const long long v = atoll(t);
