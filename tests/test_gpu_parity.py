@@ -428,6 +428,30 @@ def test_slab_per_process_api_on_one_rank(gpu, pkg, orc):
     lat.close()
 
 
+@pytest.mark.parametrize("kernel", [401, 404, 514])
+def test_single_launch_kernels_give_up_when_a_neighbour_never_runs(gpu, pkg, orc, monkeypatch, kernel):
+    """Two slabs of one lattice, only one of them is ever run: its resident kernel waits for the other's packets, gives up
+    after the lattice's time-out (once: later waits return at once), finishes, and lbm_sync reports LBM_ETIMEOUT -- the
+    device is not left spinning."""
+    import time
+
+    monkeypatch.setenv("LBM_HALO_TIMEOUT_MS", "300")
+    p, obst, _ = random_case(orc, 128, 48, seed=4, walls=False)
+    a = pkg.SlabLattice(to_param(p), obst[:24], 0, 24, 0, 2, 0, kernel=kernel)
+    b = pkg.SlabLattice(to_param(p), obst[24:], 24, 48, 1, 2, 0, kernel=kernel)
+    ha, hb = a.export_handle(), b.export_handle()
+    a.connect(hb, hb)
+    b.connect(ha, ha)
+    t0 = time.perf_counter()
+    a.run(50)
+    with pytest.raises(pkg.LbmError) as ei:
+        a.sync()
+    assert ei.value.code == 5  # LBM_ETIMEOUT
+    assert time.perf_counter() - t0 < 20.0
+    a.close()
+    b.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # the host program, end to end, with check.py's rule
 # ---------------------------------------------------------------------------------------------
