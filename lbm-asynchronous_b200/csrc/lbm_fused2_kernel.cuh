@@ -234,8 +234,6 @@ __global__ void __launch_bounds__(32 * R, MINB)
     constexpr int RB = R + 2;                          // ring rows of intermediate results
     constexpr int STAGE = stage_floats(SROWS);         // floats per stage
     constexpr uint32_t STAGE_BYTES = stage_tx_bytes(SROWS);
-    constexpr int NTHREADS = 32 * R;
-    constexpr int SPI = R / SROWS;                     // stages per iteration
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stages = reinterpret_cast<float*>(smem_raw);            // [NSTAGES][STAGE]
     const uint32_t stages_s = smem_u32(stages);
