@@ -125,7 +125,7 @@ struct Slab {
     size_t cl_smem = 0;
     // whole runs in one cooperative launch of step_ll_kernel: a row per CTA, cells in registers, packets through L2
     bool use_ll = false;
-    int ll_var = 0;              // 0: one cell per thread, 1: four
+    int ll_var = 0;              // 0: one cell per thread, 1: four, 2: two
     int ll_block = 0;
     size_t ll_smem = 0;
     uint4* ll_packets = nullptr; // [2 directions][2 parities][rows][pitch]
@@ -181,8 +181,8 @@ struct lbm_lattice {
     int loop_resident[2] = {0, 0};
     void (*band_kernel)(BandArgs) = nullptr;       // step_band_kernel (null: not available for this lattice)
     int band_block = 0, band_resident = 0;
-    void (*ll_kernel[2])(LLArgs) = {nullptr, nullptr}; // step_ll_kernel, 1 / 4 cells per thread (null: not available)
-    int ll_resident[2] = {0, 0};                   // resident CTAs per SM at the lattice's row length
+    void (*ll_kernel[3])(LLArgs) = {nullptr, nullptr, nullptr}; // step_ll_kernel, 1 / 4 / 2 cells per thread (null: not available)
+    int ll_resident[3] = {0, 0, 0};                   // resident CTAs per SM at the lattice's row length
     unsigned ll_flags = 0;                         // packet flags handed out so far (never reused)
     void (*cluster_kernel)(ClusterArgs) = nullptr; // step_cluster_kernel (null: not available for this lattice)
     int cl_cpt = 0, cl_vert = 0, cl_maxt = 0;      // its cells per thread, collision shape, thread limit
@@ -325,10 +325,12 @@ bool cluster_by_shape(int cpt, int vert, int maxt, ClusterChoice* c)
 //   400          step_ll_kernel (all steps of a run in one cooperative launch, a row per CTA, cells in registers, rows
 //                exchanging flagged 16-byte packets through L2, slabs on several GPUs through each other's memory); also
 //                the default for slabs of up to LL_MAX_CELLS cells (one cell per thread, nx <= 1024) or LL4_MAX_CELLS
-//                cells (four cells per thread, nx <= 1024) whose rows are all resident at once.  401 / 404 force one /
-//                four cells per thread
+//                cells (two cells per thread, nx <= 1024) whose rows are all resident at once.  401 / 404 / 402 force one /
+//                four / two cells per thread
 constexpr long long LL_MAX_CELLS = 70000;   // up to 256 x 256: one cell per thread
-constexpr long long LL4_MAX_CELLS = 300000; // up to 1024 x 256 (a quarter of the shipped 1024 x 1024 case): four
+constexpr int LL_CPT[3] = {1, 4, 2};           // cells per thread of step_ll_kernel's variants
+constexpr int LL_MAXT[3] = {1024, 256, 512};   // their thread limits
+constexpr long long LL4_MAX_CELLS = 300000; // up to 1024 x 256 (a quarter of the shipped 1024 x 1024 case): two
 constexpr int LL_SLOTS = 8;               // slots of the per-step sums (one RED per CTA, step and word)
 constexpr long long CLUSTER_MAX_CELLS = 32768; // 128 x 256: above, 16 SMs have more arithmetic than the whole GPU has latency
 constexpr int CLUSTER_MAX_CTAS = 16;
@@ -358,7 +360,7 @@ KernelChoice choose_kernel(const lbm_options_t& o, int nx)
     KernelChoice k;
     k.vec4 = (nx % 4 == 0) && o.kernel != 99;
     const bool band_code = (o.kernel >= 500 && o.kernel < 600);
-    const bool ll_code = (o.kernel == 400 || o.kernel == 401 || o.kernel == 404);
+    const bool ll_code = (o.kernel == 400 || o.kernel == 401 || o.kernel == 402 || o.kernel == 404);
     const bool cl_code = (o.kernel >= 3000 && o.kernel < 4000) || ll_code || band_code; // everything else as the default
     k.band = k_band_default(o.kernel) || band_code;
     k.band_block = 128, k.band_minb = 4;
@@ -508,17 +510,23 @@ void slab_geometry(lbm_lattice* L, Slab& s, const KernelChoice& k)
     // the nominal slab height
     s.use_ll = false;
     {
-        const bool ll_asked = (L->opt.kernel == 400 || L->opt.kernel == 401 || L->opt.kernel == 404);
+        const bool ll_asked = (L->opt.kernel == 400 || L->opt.kernel == 401 || L->opt.kernel == 402 || L->opt.kernel == 404);
         const int nominal_rows = (L->p.ny + total_slabs - 1) / total_slabs;
         const bool halo_ok = !uses_halo_cfg(L) || (L->opt.halo_mode == LBM_HALO_SYNC && L->opt.halo_lag == 0);
         if (k.ll && L->opt.use_graph && !L->interleaved && halo_ok) {
-            for (int v = 0; v < 2 && !s.use_ll; v++) {
+            // one cell per thread for the smallest grids, two beyond (1024 x 256: 4.6 us per step against 6.1 with four
+            // and 5.3 from step_loop_kernel); four on request only
+            const int order[3] = {0, 2, 1};
+            for (int oi = 0; oi < 3 && !s.use_ll; oi++) {
+                const int v = order[oi];
                 if (!L->ll_kernel[v]) continue;
                 if (L->opt.kernel == 401 && v != 0) continue;
                 if (L->opt.kernel == 404 && v != 1) continue;
+                if (L->opt.kernel == 402 && v != 2) continue;
+                if (v == 1 && L->opt.kernel != 404) continue;
                 if (!ll_asked && nominal_cells > (v ? LL4_MAX_CELLS : LL_MAX_CELLS)) continue;
                 if (static_cast<long long>(L->ll_resident[v]) * L->sm_count < nominal_rows) continue;
-                const int block = (L->p.nx / (v ? 4 : 1) + 31) / 32 * 32;
+                const int block = (L->p.nx / LL_CPT[v] + 31) / 32 * 32;
                 s.use_ll = true;
                 s.ll_var = v;
                 s.ll_block = block;
@@ -1152,13 +1160,15 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
     }
     if (k.ll && !L->interleaved) {
         const bool halo = uses_halo_cfg(L);
-        void (*fn[2])(LLArgs);
+        void (*fn[3])(LLArgs);
         if (halo) {
             fn[0] = strict ? step_ll_kernel<true, 1, false, 1024, 1, true> : step_ll_kernel<false, 1, false, 1024, 1, true>;
             fn[1] = strict ? step_ll_kernel<true, 4, false, 256, 2, true> : step_ll_kernel<false, 4, false, 256, 2, true>;
+            fn[2] = strict ? step_ll_kernel<true, 2, false, 512, 2, true> : step_ll_kernel<false, 2, false, 512, 2, true>;
         } else {
             fn[0] = strict ? step_ll_kernel<true, 1, false, 1024, 1, false> : step_ll_kernel<false, 1, false, 1024, 1, false>;
             fn[1] = strict ? step_ll_kernel<true, 4, false, 256, 2, false> : step_ll_kernel<false, 4, false, 256, 2, false>;
+            fn[2] = strict ? step_ll_kernel<true, 2, false, 512, 2, false> : step_ll_kernel<false, 2, false, 512, 2, false>;
         }
         for (int i = 0; i < L->nslabs; i++) {
             CU(cudaSetDevice(L->slabs[i].device));
@@ -1166,10 +1176,10 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
             CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, L->slabs[i].device));
             CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, L->slabs[i].device));
             if (i == 0 || sms < L->sm_count) L->sm_count = sms;
-            for (int v = 0; v < 2; v++) {
-                const int cpt = v ? 4 : 1;
+            for (int v = 0; v < 3; v++) {
+                const int cpt = LL_CPT[v];
                 int resident = 0;
-                if (coop && params->nx % cpt == 0 && params->nx / cpt <= (v ? 256 : 1024)) {
+                if (coop && params->nx % cpt == 0 && params->nx / cpt <= LL_MAXT[v]) {
                     const int block = (params->nx / cpt + 31) / 32 * 32;
                     const size_t smem = (2 * 6 * static_cast<size_t>(block) + 2 * (block / 32) * 4) * sizeof(float);
                     CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn[v]), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -1178,7 +1188,7 @@ int common_setup(lbm_lattice* L, const lbm_param_t* params, const lbm_options_t*
                 if (i == 0 || resident < L->ll_resident[v]) L->ll_resident[v] = resident;
             }
         }
-        for (int v = 0; v < 2; v++) L->ll_kernel[v] = L->ll_resident[v] > 0 ? fn[v] : nullptr;
+        for (int v = 0; v < 3; v++) L->ll_kernel[v] = L->ll_resident[v] > 0 ? fn[v] : nullptr;
     }
     if (k.cluster && !L->interleaved && !uses_halo_cfg(L) && L->nslabs == 1) {
         // one cluster of C CTAs (a power of two <= 16 and <= rows), rows dealt out in blocks of rpc = ceil(rows / C)

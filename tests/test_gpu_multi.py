@@ -71,9 +71,9 @@ def test_resident_step_loop_across_gpus(ngpu, pkg, orc):
         assert launches < 100 * n  # set-up kernels plus a handful of cooperative launches, not one per step
 
 
-@pytest.mark.parametrize("kernel", [401, 404, 514])
+@pytest.mark.parametrize("kernel", [401, 402, 404, 514])
 def test_packet_kernel_across_gpus(ngpu, pkg, orc, kernel):
-    """step_ll_kernel (401, 404) / step_band_kernel (514) on every GPU at once: rows inside a slab exchange packets through L2
+    """step_ll_kernel (401, 402, 404: one, two, four cells per thread) / step_band_kernel (514) on every GPU at once: rows inside a slab exchange packets through L2
     (or bands their rows), the slabs' boundary
     rows through each other's memory over NVLink (st / ld.relaxed.sys.b128), every run seeded with the packets of
     the current state.  Same bits as one GPU, also over several lbm_run calls, on a shipped case whose periodic wrap

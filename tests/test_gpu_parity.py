@@ -97,6 +97,7 @@ def exact_tot_u(orc, p, obst, cells_before, k):
     # the same with four cells per thread (packed collision, four packets per direction)
     (128, 128, 404, 0), (1024, 256, 404, 0), (256, 37, 404, 0), (8, 12, 404, 0), (4, 5, 404, 0), (100, 30, 404, 0),
     (36, 21, 404, 0), (512, 280, 404, 0), (1024, 2, 404, 0),
+    (1024, 256, 402, 0), (128, 128, 402, 0), (100, 30, 402, 0), (6, 5, 402, 0), (258, 40, 402, 0),
     # step_band_kernel (a band of rows per CTA, neighbour flags): bands of one row, ragged bands, several passes per row
     (1024, 700, 500, 0), (256, 37, 522, 0), (128, 128, 514, 0), (4096, 200, 521, 0), (12, 9, 500, 0), (64, 64, 522, 0),
     (640, 300, 514, 0), (128, 2, 500, 0), (256, 5, 541, 0), (2052, 130, 500, 0), (1024, 460, 0, 0), (512, 600, 0, 0),
@@ -174,7 +175,7 @@ def test_av_vels_identical_across_kernel_variants(gpu, pkg, orc):
     p, obst, cells0 = random_case(orc, 256, 40, seed=7)
     ref = None
     for kernel, block in [(0, 0), (10, 128), (21, 512), (99, 0), (99, 128), (10823, 0), (10444, 128), (11631, 0), (201, 0), (204, 0), (3000, 0), (3202, 0),
-                          (3104, 0), (400, 0), (404, 0), (500, 0), (514, 0)]:
+                          (3104, 0), (400, 0), (402, 0), (404, 0), (500, 0), (514, 0)]:
         with pkg.Lattice(to_param(p), obst, kernel=kernel, block=block) as lat:
             lat.upload(cells0)
             lat.run(9)
@@ -428,7 +429,7 @@ def test_slab_per_process_api_on_one_rank(gpu, pkg, orc):
     lat.close()
 
 
-@pytest.mark.parametrize("kernel", [401, 404, 514])
+@pytest.mark.parametrize("kernel", [401, 402, 404, 514])
 def test_single_launch_kernels_give_up_when_a_neighbour_never_runs(gpu, pkg, orc, monkeypatch, kernel):
     """Two slabs of one lattice, only one of them is ever run: its resident kernel waits for the other's packets, gives up
     after the lattice's time-out (once: later waits return at once), finishes, and lbm_sync reports LBM_ETIMEOUT -- the
