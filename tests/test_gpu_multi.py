@@ -111,7 +111,7 @@ def test_packet_kernel_one_process_per_gpu(ngpu, built, tmp_path):
     """The same through the per-process front end (torchrun, packet areas mapped through CUDA IPC)."""
     out = tmp_path / "result.npz"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29613", os.path.join(ROOT, "tests", "sharded_worker.py"), str(out), "128x256", "404"]
+           "--master-port", "29613", os.path.join(ROOT, "tests", "sharded_worker.py"), str(out), "128x256", "402"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = np.load(out)

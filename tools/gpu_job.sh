@@ -1,6 +1,5 @@
 #!/bin/bash
 # scratch job script for gpurun (rewritten per call)
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests -m gpu -q -x > gpurun_out/r02n_gputest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/r02n_gputest.txt
-tail -n 4 gpurun_out/r02n_gputest.txt
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
+timeout 200 python -m pytest tests/test_gpu_multi.py -m gpu -q -k "one_process_per_gpu" > gpurun_out/r02o_perprocess.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/r02o_perprocess.txt
+tail -n 4 gpurun_out/r02o_perprocess.txt
