@@ -20,8 +20,11 @@
 //     sums in shared memory are added up one step later by three threads and go to sums[step][slot] with one RED each;
 //   * accelerate-at-store as in the other kernels (applied before the exchange); the last step of the launch stores
 //     the cell to the destination lattice in global memory.
-//   * CPT = 4: a thread owns four consecutive cells (packed collision of lbm_collide4.cuh, four packets per direction):
-//     rows of up to 4096 cells, a quarter of the threads -- grids with more rows than CTAs of nx threads can be resident;
+//   * CPT = 2 / 4: a thread owns two / four consecutive cells (packed collision of lbm_collide4.cuh in two halves, CPT
+//     packets per direction): a half / a quarter of the threads per row, so grids with more rows than CTAs of nx threads
+//     can be resident.  Two cells per thread (512 threads for a 1024-cell row at 64 registers, two CTAs per SM) is the
+//     default beyond the smallest grids: twice the warps of the four-cell variant for the same instructions per cell
+//     (1024 x 256: 4.6 us per step against 6.1, profiles/r02_small_grids.md);
 //   * row slabs on several GPUs (HALO): the slab's first / last row store their packets straight into the neighbour
 //     GPU's packet area (peer memory over NVLink, st.relaxed.sys.b128) and poll their own, which the neighbour
 //     writes -- the same protocol at system scope, replacing MPI_Isend/Irecv/Waitall of MPI_Waitall/d2q9-bgk.c:225-253
